@@ -1,0 +1,185 @@
+/* gel.c -- headless `gel`: the reference's host flow (main.c:486-531) with the per-frame render path
+ * (main.c:505-522) handed to the GPU through the C ABI in include/gelcu.h.
+ *
+ *   reference main()                          here
+ *   ----------------------------------------  -------------------------------------------------------
+ *   oload / oparse / tvgen / ttgen / tngen    gel_obj_load                        (gel_host.c)
+ *   sload                                     gel_bmp_load
+ *   ssetup(800, 600)                          gelcu_create(device, xres, yres)    default 800x600, --res
+ *   iinit / ipump (mouse)                     scripted input: --mouse DX,DY per frame, or --sweep N
+ *   slock .. reset .. tdraw loop .. sunlock   gelcu_render(views...)
+ *   schurn / spresent                         per-frame JSON line (FNV-1a-64, non-zero pixels), optional
+ *                                             raw dump (--dump) or upright PPM (--ppm)
+ *   60 fps cap                                none (headless)
+ *
+ * Exit status and messages follow the reference: wrong argument count prints the usage line and returns
+ * 1 (main.c:488-492); an unreadable OBJ prints "could not open <path>" and exits 1 (main.c:463-467).
+ * There is no CPU render fallback: without a CUDA device the program fails.
+ */
+#define _DEFAULT_SOURCE
+#include "gel_host.h"
+#include "gelcu.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef struct
+{
+    int device, first, count, xres, yres, batch, readback;
+    const GelMesh* mesh; const GelTexture* tex; const gelcu_view* views;
+    uint32_t* pixels;        /* count frames (readback) */
+    uint64_t* hashes;        /* 2 per view */
+    float device_ms; double wall_s; int rc; char err[512];
+    gelcu_stats stats;
+}
+Shard;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void* shard_main(void* arg)
+{
+    Shard* s = (Shard*) arg;
+    gelcu_ctx* ctx = NULL;
+    s->rc = gelcu_create(&ctx, s->device, s->xres, s->yres);
+    if(s->rc == 0) s->rc = gelcu_set_mesh(ctx, s->mesh->tv, s->mesh->tn, s->mesh->tt, s->mesh->ntri);
+    if(s->rc == 0) s->rc = gelcu_set_texture(ctx, s->tex->pixels, s->tex->w, s->tex->h);
+    if(s->rc == 0 && s->batch > 0) s->rc = gelcu_set_option(ctx, "batch_views", s->batch);
+    if(s->rc == 0)
+    {
+        const double t0 = now_s();
+        s->rc = gelcu_render(ctx, s->views + s->first, s->count, s->readback ? s->pixels : NULL, NULL, s->hashes, &s->device_ms);
+        s->wall_s = now_s() - t0;
+        gelcu_get_stats(ctx, &s->stats);
+    }
+    if(s->rc != 0) snprintf(s->err, sizeof s->err, "%s", gelcu_last_error());
+    gelcu_destroy(ctx);
+    return NULL;
+}
+
+int main(int argc, char* argv[])
+{
+    const char* positional[2] = { NULL, NULL };
+    int npos = 0, xres = 800, yres = 600, frames = 1, dx = 0, dy = 0, sweep = 0, gpus = 1, batch = 0, readback = 1;
+    const char* dump_path = NULL; const char* ppm_prefix = NULL;
+    for(int i = 1; i < argc; i++)
+    {
+        if(!strcmp(argv[i], "--res") && i + 1 < argc) { if(sscanf(argv[++i], "%dx%d", &xres, &yres) != 2) npos = 99; }
+        else if(!strcmp(argv[i], "--frames") && i + 1 < argc) frames = atoi(argv[++i]);
+        else if(!strcmp(argv[i], "--mouse") && i + 1 < argc) { if(sscanf(argv[++i], "%d,%d", &dx, &dy) != 2) npos = 99; }
+        else if(!strcmp(argv[i], "--sweep") && i + 1 < argc) sweep = atoi(argv[++i]);
+        else if(!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
+        else if(!strcmp(argv[i], "--batch") && i + 1 < argc) batch = atoi(argv[++i]);
+        else if(!strcmp(argv[i], "--dump") && i + 1 < argc) dump_path = argv[++i];
+        else if(!strcmp(argv[i], "--ppm") && i + 1 < argc) ppm_prefix = argv[++i];
+        else if(!strcmp(argv[i], "--no-readback")) readback = 0;
+        else if(argv[i][0] == '-' && argv[i][1] == '-') npos = 99;
+        else if(npos < 2) positional[npos++] = argv[i];
+        else npos = 99;
+    }
+    if(npos != 2)
+    {
+        puts("args: path/to/obj path/to/bmp");
+        puts("      [--res WxH] [--frames N] [--mouse DX,DY] [--sweep N] [--gpus G] [--batch B]");
+        puts("      [--dump frames.raw] [--ppm prefix] [--no-readback]");
+        return 1;
+    }
+    GelMesh mesh; GelTexture tex;
+    int rc = gel_obj_load(positional[0], &mesh);
+    if(rc == -1) { printf("could not open %s\n", positional[0]); exit(1); }
+    if(rc != 0) { printf("could not parse %s (error %d)\n", positional[0], rc); exit(1); }
+    rc = gel_bmp_load(positional[1], &tex);
+    if(rc != 0) { printf("could not load %s (error %d; need a 24-bit uncompressed BMP)\n", positional[1], rc); exit(1); }
+
+    /* scripted input -> one basis per frame (main.c:501, 506-512) */
+    const int nviews = sweep > 0 ? sweep : frames;
+    if(nviews <= 0 || gpus <= 0) { puts("nothing to render"); return 1; }
+    gelcu_view* views = (gelcu_view*) malloc(sizeof(gelcu_view) * (size_t) nviews);
+    float xt = 0.0f, yt = 0.0f;
+    for(int k = 0; k < nviews; k++)
+    {
+        if(sweep > 0) { xt = (float) (2.0 * M_PI * k / sweep); yt = 0.0f; }
+        gel_view_basis(xt, yt, (float*) &views[k]);
+        if(sweep == 0) gel_input_step(&xt, &yt, dx, dy);
+    }
+    const int ndev = gelcu_device_count();
+    if(ndev <= 0) { printf("no CUDA device: %s\n", gelcu_last_error()); exit(1); }
+    if(gpus > ndev) gpus = ndev;
+    if(gpus > nviews) gpus = nviews;
+
+    const size_t frame = (size_t) xres * yres;
+    FILE* dump = dump_path ? fopen(dump_path, "wb") : NULL;
+    /* frames come back in chunks so that long sweeps do not need nviews frames of host memory */
+    const int chunk = readback ? (int) (((size_t) 1 << 30) / (frame * 4) > 0 ? ((size_t) 1 << 30) / (frame * 4) : 1) : nviews;
+    uint64_t* hashes = (uint64_t*) calloc((size_t) 2 * nviews, sizeof(uint64_t));
+    double dev_ms_max_sum = 0.0, wall_sum = 0.0;
+    uint64_t launches = 0;
+    int status = 0;
+    for(int base = 0; base < nviews; base += chunk * gpus)
+    {
+        const int n = nviews - base < chunk * gpus ? nviews - base : chunk * gpus;
+        Shard shards[64]; pthread_t th[64];
+        const int g_used = gpus > 64 ? 64 : gpus;
+        uint32_t* pixels = NULL;
+        if(readback && gelcu_host_alloc((void**) &pixels, frame * 4 * (size_t) n) != 0) { printf("host alloc failed: %s\n", gelcu_last_error()); exit(1); }
+        for(int g = 0; g < g_used; g++)
+        {
+            const int lo = (int) ((long long) n * g / g_used), hi = (int) ((long long) n * (g + 1) / g_used);
+            Shard s = { g, base + lo, hi - lo, xres, yres, batch, readback, &mesh, &tex, views,
+                        readback ? pixels + frame * lo : NULL, hashes + 2 * (size_t) (base + lo), 0.0f, 0.0, 0, "", { 0 } };
+            shards[g] = s;
+            pthread_create(&th[g], NULL, shard_main, &shards[g]);
+        }
+        float ms_max = 0.0f; double wall_max = 0.0;
+        for(int g = 0; g < g_used; g++)
+        {
+            pthread_join(th[g], NULL);
+            if(shards[g].rc < 0) { printf("gpu %d: %s\n", g, shards[g].err); exit(1); }
+            if(shards[g].rc > 0) { fprintf(stderr, "gpu %d warning: %s\n", g, shards[g].err); status = 2; }
+            if(shards[g].device_ms > ms_max) ms_max = shards[g].device_ms;
+            if(shards[g].wall_s > wall_max) wall_max = shards[g].wall_s;
+            launches += shards[g].stats.kernels_launched;
+        }
+        dev_ms_max_sum += ms_max; wall_sum += wall_max;
+        for(int k = 0; k < n; k++)
+        {
+            if(readback)
+            {
+                const uint32_t* px = pixels + frame * k;
+                size_t nonzero = 0;
+                for(size_t i = 0; i < frame; i++) nonzero += px[i] != 0;
+                printf("{\"frame\": %d, \"fnv\": \"%016llx\", \"nonzero\": %zu, \"checksum\": \"%016llx\"}\n", base + k,
+                       (unsigned long long) gel_fnv1a64_words(px, frame), nonzero, (unsigned long long) hashes[2 * (size_t) (base + k)]);
+                if(dump) fwrite(px, 4, frame, dump);
+                if(ppm_prefix)
+                {
+                    char path[1024];
+                    snprintf(path, sizeof path, "%s%04d.ppm", ppm_prefix, base + k);
+                    gel_write_ppm(path, px, xres, yres);
+                }
+            }
+            else
+                printf("{\"frame\": %d, \"checksum\": \"%016llx\", \"zchecksum\": \"%016llx\"}\n", base + k,
+                       (unsigned long long) hashes[2 * (size_t) (base + k)], (unsigned long long) hashes[2 * (size_t) (base + k) + 1]);
+        }
+        gelcu_host_free(pixels);
+    }
+    if(dump) fclose(dump);
+    printf("{\"summary\": true, \"views\": %d, \"triangles\": %d, \"res\": \"%dx%d\", \"gpus\": %d, \"device_ms\": %.4f, "
+           "\"frames_per_s_device\": %.2f, \"mtri_per_s_device\": %.3f, \"wall_s\": %.4f, \"gpu_launches\": %llu}\n",
+           nviews, mesh.ntri, xres, yres, gpus, dev_ms_max_sum,
+           dev_ms_max_sum > 0 ? nviews / (dev_ms_max_sum * 1e-3) : 0.0,
+           dev_ms_max_sum > 0 ? (double) mesh.ntri * nviews / (dev_ms_max_sum * 1e-3) / 1e6 : 0.0, wall_sum,
+           (unsigned long long) launches);
+    free(hashes); free(views);
+    gel_mesh_free(&mesh); gel_texture_free(&tex);
+    return status;
+}

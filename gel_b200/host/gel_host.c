@@ -1,0 +1,250 @@
+/* gel_host.c -- see gel_host.h.  From-scratch host flow; accepts the same OBJ grammar as the reference's
+ * oparse (main.c:129-180): lines dispatched on "vn", "vt", other 'v', 'f'; three floats per vertex line;
+ * faces are exactly `f v/t/n v/t/n v/t/n` with 1-based indices.  Numbers go through strtof/strtol, the
+ * conversions glibc's sscanf("%f"/"%d") itself performs, so parsed values are bit-identical.
+ * Differences, all in territory where the reference has undefined behaviour: a vertex line with fewer than
+ * three numbers yields zeros for the missing ones (the reference leaves stale stack values), and an index
+ * outside the arrays is an error (the reference reads out of bounds).
+ */
+#define _DEFAULT_SOURCE
+#include "gel_host.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float* p; size_t n, cap; } FVec;
+typedef struct { int* p; size_t n, cap; } IVec;
+
+static int fvec_push3(FVec* v, const float* x)
+{
+    if(v->n + 3 > v->cap)
+    {
+        const size_t cap = v->cap ? v->cap * 2 : 384;
+        float* q = (float*) realloc(v->p, cap * sizeof(float));
+        if(!q) return -1;
+        v->p = q; v->cap = cap;
+    }
+    memcpy(v->p + v->n, x, 3 * sizeof(float));
+    v->n += 3;
+    return 0;
+}
+
+static int ivec_push9(IVec* v, const int* x)
+{
+    if(v->n + 9 > v->cap)
+    {
+        const size_t cap = v->cap ? v->cap * 2 : 1152;
+        int* q = (int*) realloc(v->p, cap * sizeof(int));
+        if(!q) return -1;
+        v->p = q; v->cap = cap;
+    }
+    memcpy(v->p + v->n, x, 9 * sizeof(int));
+    v->n += 9;
+    return 0;
+}
+
+static void scan3f(const char* s, float* out)
+{
+    out[0] = out[1] = out[2] = 0.0f;
+    for(int k = 0; k < 3; k++)
+    {
+        char* end;
+        const float f = strtof(s, &end);
+        if(end == s) return;
+        out[k] = f;
+        s = end;
+    }
+}
+
+/* `f %d/%d/%d %d/%d/%d %d/%d/%d` -> q[9] in file order; returns the number of integers converted */
+static int scan_face(const char* s, int* q)
+{
+    int got = 0;
+    for(int k = 0; k < 9; k++)
+    {
+        char* end;
+        const long v = strtol(s, &end, 10);
+        if(end == s) break;
+        q[k] = (int) v; got++;
+        s = end;
+        if(k % 3 != 2) { if(*s != '/') break; s++; }
+    }
+    return got;
+}
+
+int gel_obj_load(const char* path, GelMesh* out)
+{
+    memset(out, 0, sizeof *out);
+    FILE* f = fopen(path, "r");
+    if(!f) return -1;
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    char* text = (char*) malloc((size_t) size + 1);
+    if(!text) { fclose(f); return -3; }
+    const size_t got = fread(text, 1, (size_t) size, f);
+    fclose(f);
+    text[got] = '\0';
+
+    FVec vs = { 0 }, ns = { 0 }, ts = { 0 };
+    IVec fs = { 0 };
+    int rc = 0;
+    for(char* line = text; line < text + got && rc == 0; )
+    {
+        char* nl = (char*) memchr(line, '\n', (size_t) (text + got - line));
+        if(nl) *nl = '\0';
+        float v[3];
+        if(line[0] == 'v' && line[1] == 'n') { scan3f(line + 2, v); rc = fvec_push3(&ns, v); }
+        else if(line[0] == 'v' && line[1] == 't') { scan3f(line + 2, v); rc = fvec_push3(&ts, v); }
+        else if(line[0] == 'v') { scan3f(line + 1, v); rc = fvec_push3(&vs, v); }
+        else if(line[0] == 'f')
+        {
+            int q[9];
+            if(scan_face(line + 1, q) == 9)
+            {
+                for(int k = 0; k < 9; k++) q[k] -= 1;
+                rc = ivec_push9(&fs, q);
+            }
+            else rc = -2;
+        }
+        if(!nl) break;
+        line = nl + 1;
+    }
+    free(text);
+    if(rc) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return rc == -2 ? -2 : -3; }
+
+    const int nv = (int) (vs.n / 3), nvn = (int) (ns.n / 3), nvt = (int) (ts.n / 3), nt = (int) (fs.n / 9);
+    /* vmaxlen (main.c:233-240) and tvgen's integer scale (main.c:244) */
+    float maxlen = 0.0f;
+    for(int i = 0; i < nv; i++)
+    {
+        const float* p = vs.p + 3 * i;
+        const float len = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        if(len > maxlen) maxlen = len;
+    }
+    const int scale = (int) maxlen;
+    if(nt > 0 && scale == 0) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return -4; }
+    const float inv = nt > 0 ? 1.0f / scale : 1.0f;
+    out->tv = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
+    out->tn = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
+    out->tt = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
+    if(!out->tv || !out->tn || !out->tt) rc = -3;
+    for(int i = 0; i < nt && rc == 0; i++)
+        for(int k = 0; k < 3; k++)
+        {
+            const int* q = fs.p + 9 * (size_t) i + 3 * k;   /* v, t, n of corner k */
+            if(q[0] < 0 || q[0] >= nv || q[1] < 0 || q[1] >= nvt || q[2] < 0 || q[2] >= nvn) { rc = -2; break; }
+            for(int e = 0; e < 3; e++)
+            {
+                out->tv[9 * (size_t) i + 3 * k + e] = vs.p[3 * q[0] + e] * inv;
+                out->tt[9 * (size_t) i + 3 * k + e] = ts.p[3 * q[1] + e];
+                out->tn[9 * (size_t) i + 3 * k + e] = ns.p[3 * q[2] + e];
+            }
+        }
+    free(vs.p); free(ns.p); free(ts.p); free(fs.p);
+    if(rc) { gel_mesh_free(out); return rc; }
+    out->ntri = nt; out->nv = nv; out->nvt = nvt; out->nvn = nvn;
+    return 0;
+}
+
+void gel_mesh_free(GelMesh* m)
+{
+    free(m->tv); free(m->tn); free(m->tt);
+    memset(m, 0, sizeof *m);
+}
+
+static uint32_t le32(const unsigned char* p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t) p[3] << 24; }
+
+int gel_bmp_load(const char* path, GelTexture* out)
+{
+    memset(out, 0, sizeof *out);
+    FILE* f = fopen(path, "rb");
+    if(!f) return -1;
+    unsigned char hdr[54];
+    if(fread(hdr, 1, 54, f) != 54 || hdr[0] != 'B' || hdr[1] != 'M') { fclose(f); return -2; }
+    const uint32_t data_off = le32(hdr + 10);
+    const int32_t w = (int32_t) le32(hdr + 18), hs = (int32_t) le32(hdr + 22);
+    const int bpp = hdr[28] | hdr[29] << 8;
+    if(bpp != 24 || le32(hdr + 30) != 0 || w <= 0 || hs == 0) { fclose(f); return -2; }
+    const int h = hs < 0 ? -hs : hs;
+    const size_t stride = ((size_t) w * 3 + 3) & ~(size_t) 3;
+    unsigned char* row = (unsigned char*) malloc(stride);
+    uint32_t* px = (uint32_t*) malloc(sizeof(uint32_t) * (size_t) w * h);
+    if(!row || !px) { free(row); free(px); fclose(f); return -3; }
+    fseek(f, (long) data_off, SEEK_SET);
+    for(int r = 0; r < h; r++)
+    {
+        if(fread(row, 1, stride, f) != stride) { free(row); free(px); fclose(f); return -4; }
+        uint32_t* dst = px + (size_t) (hs < 0 ? r : h - 1 - r) * w;    /* file is bottom-up unless height < 0 */
+        for(int x = 0; x < w; x++)
+            dst[x] = (uint32_t) row[3 * x + 2] << 16 | (uint32_t) row[3 * x + 1] << 8 | row[3 * x];   /* X byte = 0 */
+    }
+    free(row);
+    fclose(f);
+    out->pixels = px; out->w = w; out->h = h;
+    return 0;
+}
+
+void gel_texture_free(GelTexture* t) { free(t->pixels); memset(t, 0, sizeof *t); }
+
+void gel_view_basis(float xt, float yt, float basis[12])
+{
+    float* x = basis; float* y = basis + 3; float* z = basis + 6; float* eye = basis + 9;
+    eye[0] = sinf(xt); eye[1] = sinf(yt); eye[2] = cosf(xt);                       /* main.c:509 */
+    /* z = vunit(vsub(eye, center)), center = 0                                       main.c:510 */
+    const float dx = eye[0] - 0.0f, dy = eye[1] - 0.0f, dz = eye[2] - 0.0f;
+    const float iz = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    z[0] = dx * iz; z[1] = dy * iz; z[2] = dz * iz;
+    /* x = vunit(vcross(upward, z)), upward = (0,1,0)                                 main.c:511 */
+    const float ux = 0.0f, uy = 1.0f, uz = 0.0f;
+    const float cx = uy * z[2] - uz * z[1], cy = uz * z[0] - ux * z[2], cz = ux * z[1] - uy * z[0];
+    const float ix = 1.0f / sqrtf(cx * cx + cy * cy + cz * cz);
+    x[0] = cx * ix; x[1] = cy * ix; x[2] = cz * ix;
+    /* y = vcross(z, x)                                                                main.c:512 */
+    y[0] = z[1] * x[2] - z[2] * x[1];
+    y[1] = z[2] * x[0] - z[0] * x[2];
+    y[2] = z[0] * x[1] - z[1] * x[0];
+}
+
+void gel_input_step(float* xt, float* yt, int dx, int dy)
+{
+    const float sens = 0.005f;
+    *xt -= sens * dx;
+    *yt += sens * dy;
+}
+
+uint64_t gel_fnv1a64_words(const uint32_t* w, uint64_t n)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for(uint64_t i = 0; i < n; i++) h = (h ^ w[i]) * 0x100000001b3ull;
+    return h;
+}
+
+void gel_upright(const uint32_t* canvas, int xres, int yres, uint32_t* upright)
+{
+    for(int wy = 0; wy < yres; wy++)
+        for(int wx = 0; wx < xres; wx++)
+            upright[(size_t) wy * xres + wx] = canvas[(size_t) (yres - 1 - wy) + (size_t) wx * yres];
+}
+
+int gel_write_ppm(const char* path, const uint32_t* canvas, int xres, int yres)
+{
+    FILE* f = fopen(path, "wb");
+    if(!f) return -1;
+    fprintf(f, "P6\n%d %d\n255\n", xres, yres);
+    unsigned char* row = (unsigned char*) malloc((size_t) 3 * xres);
+    for(int wy = 0; wy < yres; wy++)
+    {
+        for(int wx = 0; wx < xres; wx++)
+        {
+            const uint32_t p = canvas[(size_t) (yres - 1 - wy) + (size_t) wx * yres];
+            row[3 * wx] = (unsigned char) (p >> 16); row[3 * wx + 1] = (unsigned char) (p >> 8); row[3 * wx + 2] = (unsigned char) p;
+        }
+        fwrite(row, 1, (size_t) 3 * xres, f);
+    }
+    free(row);
+    fclose(f);
+    return 0;
+}

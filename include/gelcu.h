@@ -1,0 +1,124 @@
+/* gelcu.h -- C ABI of the B200 (sm_100a) implementation of gel's per-frame render path.
+ *
+ * The reference (yellingintothefan/gel, main.c) has no plugin or FFI interface: its hot path is the code
+ * between slock() and sunlock() in the frame loop, main.c:504-523 --
+ *     reset (main.c:413-417, called at :505), camera basis (:506-512), and per triangle
+ *     tviewnrm/tviewtri/tperspective/tviewport/tdraw (:513-522).
+ * This header is the seam a maintainer would cut there (INTEGRATION.md shows the patch): the host keeps
+ * OBJ/BMP loading, soup expansion, input handling and present; one gelcu_render() call replaces :505-522.
+ *
+ * Plain C, no C++/torch types.  Every function returns GELCU_OK (0), a positive warning, or a negative
+ * error; gelcu_last_error() returns a thread-local message for the most recent non-zero return.
+ * There is NO CPU fallback: without a CUDA device gelcu_create() fails with GELCU_E_NOGPU.
+ *
+ * Threading: calls on one context must be serialised by the caller; different contexts (one per GPU)
+ * may be driven concurrently from different host threads or processes.
+ */
+#ifndef GELCU_H
+#define GELCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GELCU_OK            0
+/* Frames were produced, but some input left the domain where the reference is defined:
+ * a projected bbox left [0,xres-1]x[0,yres-1] (reference: out-of-bounds writes, main.c:344-349) or a
+ * texel coordinate left the texture (reference: out-of-bounds read, main.c:360-361,366).  The device
+ * clips / clamps instead of emulating undefined behaviour. */
+#define GELCU_W_CLIPPED     1
+#define GELCU_E_INVALID    (-1)   /* bad argument / call order                           */
+#define GELCU_E_CUDA       (-2)   /* a CUDA runtime call failed (message has the detail)  */
+#define GELCU_E_NOMEM      (-3)   /* host or device allocation failed                     */
+#define GELCU_E_NOGPU      (-4)   /* no usable CUDA device                                */
+
+typedef struct gelcu_ctx gelcu_ctx;   /* one per GPU */
+
+/* One view = the camera basis the reference builds at main.c:509-512 from (xt, yt):
+ *   eye = (sinf xt, sinf yt, cosf xt); z = unit(eye - 0); x = unit((0,1,0) x z); y = z x x.
+ * It is computed ON THE HOST (libm sinf/cosf) -- gel_view_basis() in gel_host.h -- so the CPU reference
+ * and the device consume identical floats. */
+typedef struct { float x[3], y[3], z[3], eye[3]; } gelcu_view;
+
+/* Counters of the most recent gelcu_render() call. */
+typedef struct
+{
+    uint64_t kernels_launched;   /* CUDA kernels of this library launched by the call              */
+    uint64_t views;              /* views rendered                                                 */
+    uint64_t bin_entries;        /* (triangle, tile) pairs binned, summed over views               */
+    uint64_t unique_vertices;    /* distinct (position, normal) corners the transform kernel sees  */
+    uint64_t triangles;          /* triangles per view                                             */
+    uint64_t h2d_bytes;          /* bytes copied host->device by the call (views)                  */
+    uint64_t d2h_bytes;          /* bytes copied device->host by the call (frames, z, checksums)   */
+    float    ms_transform;       /* CUDA-event time of the vertex-transform kernels                */
+    float    ms_bin;             /* ... of triangle setup + tile binning (count, scan, fill)       */
+    float    ms_raster;          /* ... of the tile rasteriser                                     */
+    float    ms_total;           /* first kernel start to last kernel end (no copies)              */
+    uint32_t flags;              /* OR of per-view device flags: 1 = bbox clipped, 2 = texel clamped */
+    uint32_t batches;            /* view batches the call was split into                           */
+}
+gelcu_stats;
+
+/* Number of CUDA devices, or a negative error. */
+int gelcu_device_count(void);
+
+/* Creates a context bound to `device` rendering at xres x yres (the reference's Sdl.xres/yres, main.c:434-445). */
+int gelcu_create(gelcu_ctx** ctx, int device, int xres, int yres);
+
+/* Mesh = the three triangle soups of main.c:496-498 (tv: positions already scaled by tvgen, tn: normals,
+ * tt: texture coordinates), 9 floats per triangle in the reference's Triangle layout (a.xyz b.xyz c.xyz,
+ * main.c:8-12,45-49).  Copied; the caller may free its arrays.  ntri may be 0. */
+int gelcu_set_mesh(gelcu_ctx* ctx, const float* tv, const float* tn, const float* tt, int ntri);
+
+/* Texture = fdif->pixels / w / h (main.c:359-361,366): XRGB8888, top-down, pitch 4*w.  Copied. */
+int gelcu_set_texture(gelcu_ctx* ctx, const uint32_t* xrgb, int w, int h);
+
+/* Renders `nviews` frames; replaces main.c:505-522 for each of them.
+ *   pixel_out  host, nviews*xres*yres uint32 in the reference's sideways order (index y + x*yres,
+ *              main.c:356,365-366,441), values 0x00RRGGBB; or NULL to leave frames on the device
+ *   z_out      host, nviews*xres*yres float (the reference's zbuff, main.c:500); or NULL
+ *   hash_out   host, 2*nviews: [2k] = checksum of view k's pixel words, [2k+1] = of its z bit patterns,
+ *              computed on the device as  sum_i mix32(word_i ^ i*0x9E3779B1) mod 2^64  with
+ *              mix32(h): h*=0x85EBCA6B; h^=h>>13; h*=0xC2B2AE35; h^=h>>16  (order-independent, so tiles
+ *              can contribute in any order); or NULL
+ *   device_ms  CUDA-event time of the kernels only (no copies), summed over batches; or NULL
+ * Host pointers may be pageable or pinned (gelcu_host_alloc); pinned buffers copy faster and overlap
+ * with rendering.  With pixel_out == z_out == NULL the last batch stays readable via gelcu_read_frame. */
+int gelcu_render(gelcu_ctx* ctx, const gelcu_view* views, int nviews,
+                 uint32_t* pixel_out, float* z_out, uint64_t* hash_out, float* device_ms);
+
+/* Copies frame `slot` (0-based within the LAST batch of the previous gelcu_render) to the host. */
+int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out);
+
+/* Tunables, by name (returns GELCU_E_INVALID for unknown names):
+ *   "batch_views"   views rendered per kernel launch set (default: sized so frames fit ~8 GB)
+ *   "raster_ctas_per_sm"   persistent rasteriser CTAs per SM (default 4)
+ *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1) */
+int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
+int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
+
+/* Stage introspection for the parity tests (not used by the render path):
+ *   gelcu_debug_transform: runs the vertex-transform kernel for one view and expands the result per
+ *       corner: vew receives 9 floats per triangle (screen x, y, z of a, b, c -- the reference's `vew`,
+ *       main.c:519), shade 3 floats per triangle (vdot(lights, nrm.{a,b,c}), main.c:358).
+ *   gelcu_debug_bins: runs transform + binning for one view; counts receives one int per screen tile
+ *       (tile = tx*tiles_y + ty), entries the triangle indices tile by tile (ascending per tile), at
+ *       most `cap` of them; *total is the number of (triangle, tile) pairs. */
+int gelcu_debug_transform(gelcu_ctx* ctx, const gelcu_view* view, float* vew, float* shade);
+int gelcu_debug_bins(gelcu_ctx* ctx, const gelcu_view* view, int* counts, int* entries, int cap, int* total);
+int gelcu_tile_grid(gelcu_ctx* ctx, int* tile_w, int* tile_h, int* tiles_x, int* tiles_y);
+
+/* Page-locked host memory for pixel_out / z_out. */
+int  gelcu_host_alloc(void** p, size_t bytes);
+void gelcu_host_free(void* p);
+
+void gelcu_destroy(gelcu_ctx* ctx);
+const char* gelcu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GELCU_H */

@@ -1,0 +1,78 @@
+/* TEST-ONLY harness: compiles gel_b200/csrc/gel_math.h for the HOST so the operation order of the device
+ * math and the keyed depth resolve (gelcu.cu) can be checked against the oracle in a container with no
+ * GPU.  It walks triangles in REVERSE submission order on purpose: the (z, index) key must make the
+ * result order-independent.  Never linked into the product; the product has no CPU path. */
+#include "../../gel_b200/csrc/gel_math.h"
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+extern "C" void emu_transform(const float* tv, const float* tn, int ntri, const float* basis, int xres, int yres,
+                              float* vew, float* shade)
+{
+    const gel::ViewConst c = gel::view_const(basis, xres, yres);
+    for(int i = 0; i < 3 * ntri; i++)
+        gel::transform_corner(c, tv[3 * i], tv[3 * i + 1], tv[3 * i + 2], tn[3 * i], tn[3 * i + 1], tn[3 * i + 2],
+                              vew[3 * i], vew[3 * i + 1], vew[3 * i + 2], shade[i]);
+}
+
+extern "C" int emu_render(const float* tv, const float* tn, const float* tt, int ntri, const uint32_t* tex, int tw, int th,
+                          int xres, int yres, const float* basis, uint32_t* pixel, float* zbuff, int use_sign_guard)
+{
+    const uint64_t CLEAR = (0x00800000ull << 32) | 0xFFFFFFFFull;
+    std::vector<float> vew(9 * (size_t) ntri), shade(3 * (size_t) ntri);
+    emu_transform(tv, tn, ntri, basis, xres, yres, vew.data(), shade.data());
+    std::vector<uint64_t> keys((size_t) xres * yres, CLEAR);
+    int flags = 0;
+    for(int t = ntri - 1; t >= 0; t--)
+    {
+        const float* p = &vew[9 * (size_t) t];
+        const gel::TriSetup s = gel::tri_setup(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+        int x0 = s.x0, y0 = s.y0, x1 = s.x1, y1 = s.y1;
+        if(x0 < 0 || y0 < 0 || x1 > xres - 1 || y1 > yres - 1) { flags |= 1; if(x0 < 0) x0 = 0; if(y0 < 0) y0 = 0; if(x1 > xres - 1) x1 = xres - 1; if(y1 > yres - 1) y1 = yres - 1; }
+        const float sden = use_sign_guard ? gel::sign_guard(s.den) : 0.0f;
+        for(int x = x0; x <= x1; x++)
+            for(int y = y0; y <= y1; y++)
+            {
+                float nv, nw, v, w, u, z;
+                gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+                if(gel::surely_negative(nv, sden) || gel::surely_negative(nw, sden)) continue;
+                if(!gel::bary_inside(s, nv, nw, v, w, u, z)) continue;
+                const uint64_t key = ((uint64_t) gel::zkey(z) << 32) | (0xFFFFFFFFu - (uint32_t) t);
+                uint64_t& k = keys[(size_t) y + (size_t) x * yres];
+                if(key > k) k = key;
+            }
+    }
+    for(int x = 0; x < xres; x++)
+        for(int y = 0; y < yres; y++)
+        {
+            const size_t idx = (size_t) y + (size_t) x * yres;
+            const uint64_t key = keys[idx];
+            uint32_t colour = 0; float z = -FLT_MAX;
+            if(key != CLEAR)
+            {
+                const uint32_t t = 0xFFFFFFFFu - (uint32_t) key;
+                z = gel::zkey_inv((uint32_t) (key >> 32));
+                const float* p = &vew[9 * (size_t) t];
+                const gel::TriSetup s = gel::tri_setup(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+                float nv, nw, v, w, u, zz;
+                gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+                gel::bary_inside(s, nv, nw, v, w, u, zz);
+                const float uv[6] = { tt[9 * (size_t) t], tt[9 * (size_t) t + 1], tt[9 * (size_t) t + 3], tt[9 * (size_t) t + 4], tt[9 * (size_t) t + 6], tt[9 * (size_t) t + 7] };
+                int xx, yy, shading;
+                gel::fragment_shade(v, w, u, uv, shade[3 * (size_t) t], shade[3 * (size_t) t + 1], shade[3 * (size_t) t + 2], tw, th, xx, yy, shading);
+                if(xx < 0 || xx > tw - 1 || yy < 0 || yy > th - 1) { flags |= 2; xx = xx < 0 ? 0 : xx > tw - 1 ? tw - 1 : xx; yy = yy < 0 ? 0 : yy > th - 1 ? th - 1 : yy; }
+                colour = gel::pshade(tex[xx + yy * tw], shading);
+            }
+            pixel[idx] = colour; zbuff[idx] = z;
+        }
+    return flags;
+}
+
+extern "C" uint64_t emu_salted_sum(const uint32_t* w, uint64_t n)
+{
+    uint64_t s = 0;
+    for(uint64_t i = 0; i < n; i++) s += gel::salt_mix(w[i], (uint32_t) i);
+    return s;
+}

@@ -1,0 +1,277 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI (include/gelcu.h), against
+ (1) the committed golden vectors made by the UNMODIFIED reference, (2) the CPU oracle on the same seeded inputs,
+ (3) size-independent properties at BASELINE.json's full sizes.  Bar: bit-exact pixels, z and checksums."""
+import os
+
+import numpy as np
+import pytest
+
+import gel_b200
+import oracle
+from conftest import bits, random_soup
+from gel_b200 import synth
+
+pytestmark = pytest.mark.gpu
+NTHREADS = max(1, min(os.cpu_count() or 1, 64))
+FLT_MIN = np.finfo(np.float32).min
+
+
+def make_renderer(xres, yres, tv, tn, tt, tex):
+    r = gel_b200.Renderer(xres, yres)
+    r.set_mesh(tv, tn, tt)
+    r.set_texture(tex)
+    return r
+
+
+def assert_views_match(r, tv, tn, tt, tex, bases, *, expect_rc=0):
+    out = r.render(bases, pixels=True, z=True, hashes=True)
+    ref = oracle.render_views(tv, tn, tt, tex, r.xres, r.yres, bases, nthreads=NTHREADS, z=True, hashes=True)
+    assert out["rc"] == expect_rc
+    bad = int((out["pixel"] != ref["pixel"]).sum())
+    assert bad == 0, f"{bad} pixels differ"
+    assert np.array_equal(bits(out["z"]), bits(ref["z"]))
+    assert np.array_equal(out["hash"], ref["hash"])
+    return out, ref
+
+
+# ---- golden vectors from the unmodified reference ---------------------------------------------------
+
+def test_golden_vectors(golden, cfg1):
+    tv, tn, tt, tex = cfg1
+    for case in golden["cases"]:
+        ang = [(np.uint32(f["xt_bits"]).view(np.float32), np.uint32(f["yt_bits"]).view(np.float32)) for f in case["frames"]]
+        with make_renderer(case["xres"], case["yres"], tv, tn, tt, tex) as r:
+            out = r.render(gel_b200.view_bases(ang), hashes=True)
+        for k, f in enumerate(case["frames"]):
+            assert "%016x" % gel_b200.fnv1a64_words(out["pixel"][k]) == f["fnv"]
+            assert int((out["pixel"][k] != 0).sum()) == f["nonzero"]
+            assert "%016x" % int(out["hash"][k, 0]) == f["salted_sum"]
+
+
+# ---- per-stage parity ---------------------------------------------------------------------------------
+
+def test_stage_transform_bits(cfg1):
+    tv, tn, tt, tex = cfg1
+    with make_renderer(1920, 1080, tv, tn, tt, tex) as r:
+        for xt, yt in [(0, 0), (1.1, 0.3), (3.3, -0.2)]:
+            basis = gel_b200.view_basis(xt, yt)
+            vew, shade = r.debug_transform(basis)
+            rvew, rnrm = oracle.transform(tv, tn, basis, 1920, 1080)
+            assert np.array_equal(bits(vew), bits(rvew))
+            n = rnrm.reshape(-1, 3, 3)
+            want = ((np.float32(0) * n[:, :, 0] + np.float32(0) * n[:, :, 1]) + np.float32(1) * n[:, :, 2]).astype(np.float32)
+            assert np.array_equal(bits(shade), bits(want))
+        assert r.stats()["unique_vertices"] == 2601          # 5 000 x 3 corners merge back to the OBJ's 2 601
+
+
+def test_stage_bins(cfg1):
+    """Per-tile triangle lists = exactly the triangles whose main.c:344-347 bbox overlaps the tile."""
+    tv, tn, tt, tex = cfg1
+    with make_renderer(800, 600, tv, tn, tt, tex) as r:
+        tw, th, ntx, nty = r.tile_grid()
+        basis = gel_b200.view_basis(0.7, 0.2)
+        counts, entries, total = r.debug_bins(basis)
+        vew, _ = oracle.transform(tv, tn, basis, 800, 600)
+        v = vew.reshape(-1, 3, 3)
+        x0 = np.minimum.reduce(v[:, :, 0], axis=1).astype(np.int32); x1 = np.maximum.reduce(v[:, :, 0], axis=1).astype(np.int32)
+        y0 = np.minimum.reduce(v[:, :, 1], axis=1).astype(np.int32); y1 = np.maximum.reduce(v[:, :, 1], axis=1).astype(np.int32)
+        want = [[] for _ in range(ntx * nty)]
+        for t in range(len(v)):
+            for tx in range(x0[t] // tw, x1[t] // tw + 1):
+                for ty in range(y0[t] // th, y1[t] // th + 1):
+                    want[tx * nty + ty].append(t)
+        assert total == sum(len(w) for w in want) == len(entries)
+        assert list(counts) == [len(w) for w in want]
+        assert list(entries) == [t for w in want for t in w]
+
+
+# ---- BASELINE.json configs ------------------------------------------------------------------------------
+
+def test_cfg1_default_resolution(cfg1):
+    tv, tn, tt, tex = cfg1
+    bases = gel_b200.view_bases([(0, 0), (0.2, 0), (0.4, 0), (2.5, -0.3), (4.0, 0.2), (-1.0, 0.45)])
+    with make_renderer(800, 600, tv, tn, tt, tex) as r:
+        out, ref = assert_views_match(r, tv, tn, tt, tex, bases)
+        assert r.stats()["kernels_launched"] == 5
+    assert int((out["pixel"][0] != 0).sum()) == 105139
+
+
+def test_cfg2_360_views_1080p(cfg1):
+    tv, tn, tt, tex = cfg1
+    bases = gel_b200.view_bases(synth.view_angles(360))
+    ref = oracle.render_views(tv, tn, tt, tex, 1920, 1080, bases, nthreads=NTHREADS, pixels=False, hashes=True)
+    with make_renderer(1920, 1080, tv, tn, tt, tex) as r:
+        out = r.render(bases, pixels=False, hashes=True)
+        assert out["rc"] == 0 and np.array_equal(out["hash"], ref["hash"])
+        r.set_option("batch_views", 7)                       # ragged batches: 51 x 7 + 3
+        out7 = r.render(bases, pixels=False, hashes=True)
+        assert np.array_equal(out7["hash"], ref["hash"]) and r.stats()["batches"] == 52
+        assert_views_match(r, tv, tn, tt, tex, bases[[0, 45, 90, 179, 180, 271, 359]])
+
+
+@pytest.fixture(scope="module")
+def cfg3_inputs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg3")
+    obj = str(d / "sphere707.obj")
+    open(obj, "w").write(synth.sphere_obj_text(707, 707))
+    bmp = str(d / "tex2048.bmp")
+    open(bmp, "wb").write(synth.texture_bmp_bytes(2048))
+    tv, tn, tt = gel_b200.load_obj(obj)
+    return tv, tn, tt, gel_b200.load_bmp(bmp)
+
+
+def test_cfg3_1m_triangles_4k(cfg3_inputs):
+    tv, tn, tt, tex = cfg3_inputs
+    assert tv.shape[0] == 999698 and tex.shape == (2048, 2048)
+    bases = gel_b200.view_bases(synth.view_angles(64)[[0, 5, 21, 40]])
+    with make_renderer(3840, 2160, tv, tn, tt, tex) as r:
+        out, ref = assert_views_match(r, tv, tn, tt, tex, bases)
+        assert r.stats()["unique_vertices"] == 501264
+    assert int((ref["z"][0] != FLT_MIN).sum()) > 1_300_000
+
+
+def test_cfg4_overdraw_and_z_ties(tmp_path):
+    obj = str(tmp_path / "overdraw.obj")
+    open(obj, "w").write(synth.overdraw_obj_text(100_000))
+    tv, tn, tt = gel_b200.load_obj(obj)
+    assert tv.shape[0] == 200_000
+    tex = np.random.default_rng(9).integers(0, 1 << 24, (256, 256), dtype=np.uint32)
+    bases = gel_b200.view_bases([(0.0, 0.0), (0.05, 0.02), (-0.08, 0.0), (0.1, -0.03)])
+    with make_renderer(1920, 1080, tv, tn, tt, tex) as r:
+        assert_views_match(r, tv, tn, tt, tex, bases)
+        # every pair is coincident: dropping the SECOND copy of each pair must not change a single pixel
+        first_only = np.arange(0, 200_000, 2)
+        r.set_mesh(tv[first_only], tn[first_only], tt[first_only])
+        single = r.render(bases[:2], z=True)
+        r.set_mesh(tv, tn, tt)
+        double = r.render(bases[:2], z=True)
+        assert np.array_equal(single["pixel"], double["pixel"]) and np.array_equal(bits(single["z"]), bits(double["z"]))
+
+
+def test_cfg5_8192_views_properties(cfg1):
+    """Full-size batch: sampled views against the oracle, idempotence, and independence from batch position."""
+    tv, tn, tt, tex = cfg1
+    n = 8192
+    bases = gel_b200.view_bases(synth.view_angles(n))
+    with make_renderer(1920, 1080, tv, tn, tt, tex) as r:
+        a = r.render(bases, pixels=False, hashes=True)
+        b = r.render(bases[::-1].copy(), pixels=False, hashes=True)
+        assert a["rc"] == 0
+        assert np.array_equal(a["hash"], b["hash"][::-1])                 # a view's frame does not depend on its slot
+        sample = np.arange(0, n, 257)
+        ref = oracle.render_views(tv, tn, tt, tex, 1920, 1080, bases[sample], nthreads=NTHREADS, pixels=False, hashes=True)
+        assert np.array_equal(a["hash"][sample], ref["hash"])
+        assert len({int(h) for h in a["hash"][:, 0]}) > n // 2            # the views really differ
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+
+def small_tex(rng, h=16, w=16):
+    return rng.integers(0, 1 << 24, (h, w), dtype=np.uint32)
+
+
+def test_empty_mesh_gives_cleared_frames():
+    z = np.zeros((0, 9), np.float32)
+    with make_renderer(200, 150, z, z, z, small_tex(np.random.default_rng(0))) as r:
+        out = r.render(gel_b200.view_bases([(0, 0), (1, 0)]), z=True, hashes=True)
+    assert not out["pixel"].any() and (out["z"] == FLT_MIN).all()
+    assert int(out["hash"][0, 0]) == oracle.salted_sum(out["pixel"][0]) and int(out["hash"][1, 1]) == oracle.salted_sum(out["z"][1])
+
+
+@pytest.mark.parametrize("res", [(200, 150), (101, 67), (33, 31), (1, 1), (640, 480)])
+def test_random_soup_odd_resolutions(res):
+    rng = np.random.default_rng(res[0] * 1000 + res[1])
+    tv, tn, tt = random_soup(rng, 800, size=(0.01, 0.2), xr=(-0.3, 0.3), yr=(-0.2, 1.0))
+    tex = small_tex(rng, 64, 32)
+    bases = gel_b200.view_bases([(0, 0), (0.3, 0.1), (-0.2, -0.1)])
+    with make_renderer(res[0], res[1], tv, tn, tt, tex) as r:
+        out = r.render(bases, z=True, hashes=True)
+        ref = oracle.render_views(tv, tn, tt, tex, res[0], res[1], bases, z=True, hashes=True)
+        assert out["rc"] == (1 if ref["clipped"] else 0)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"]))
+        assert np.array_equal(out["hash"], ref["hash"])
+
+
+def test_ties_degenerates_and_large_triangles():
+    rng = np.random.default_rng(21)
+    tv, tn, tt = random_soup(rng, 300, size=(0.005, 0.05))
+    big_v, big_n, big_t = random_soup(rng, 12, size=(0.3, 0.6), xr=(-0.2, 0.2), yr=(0.2, 0.8))       # many tiles each
+    deg = tv[:50].copy(); deg[:, 6:9] = deg[:, 3:6]                                                    # zero area
+    tv = np.vstack([tv, big_v, tv[:100], deg, big_v[:4]])
+    tn = np.vstack([tn, big_n, tn[:100], tn[:50], big_n[:4]])
+    tt = np.vstack([tt, big_t, rng.uniform(0, 1, (100, 9)).astype(np.float32), tt[:50], rng.uniform(0, 1, (4, 9)).astype(np.float32)])
+    tex = small_tex(rng, 32, 32)
+    with make_renderer(800, 600, tv, tn, tt, tex) as r:
+        assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0), (0.25, 0.05)]))
+
+
+def test_texture_corners_and_shading_clamp_ends():
+    """uv exactly 0 and 1 (texel (0, h-1) .. (w-1, 0)); normals facing away (intensity < 0 -> shading 0)."""
+    tv = np.array([[-0.4, 0.1, 0, 0.4, 0.1, 0, 0.0, 0.9, 0], [-0.4, 0.1, -0.2, 0.4, 0.1, -0.2, 0.0, 0.9, -0.2]], np.float32)
+    tn = np.array([[0, 0, 1] * 3, [0, 0, -1] * 3], np.float32)
+    tt = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0], [0, 0, 0, 1, 1, 0, 1, 0, 0]], np.float32)
+    tex = small_tex(np.random.default_rng(4), 8, 8)
+    with make_renderer(320, 240, tv, tn, tt, tex) as r:
+        out, ref = assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0), (np.pi, 0)]))
+    assert out["pixel"][0].any()
+
+
+def test_offscreen_triangles_are_clipped_and_flagged():
+    rng = np.random.default_rng(33)
+    tv, tn, tt = random_soup(rng, 200, size=(0.05, 0.3), xr=(-1.6, 1.6), yr=(-0.9, 1.9))
+    tex = small_tex(rng)
+    with make_renderer(320, 240, tv, tn, tt, tex) as r:
+        out, ref = assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0)]), expect_rc=gel_b200.GELCU_W_CLIPPED)
+        assert ref["clipped"] == 1 and r.stats()["flags"] & 1
+
+
+def test_texel_out_of_range_is_clamped_and_flagged():
+    tv = np.array([[-0.4, 0.1, 0, 0.4, 0.1, 0, 0.0, 0.9, 0]], np.float32)
+    tn = np.array([[0, 0, 1] * 3], np.float32)
+    tt = np.array([[0, 0, 0, 1.5, 0, 0, 0, 1.5, 0]], np.float32)
+    with make_renderer(320, 240, tv, tn, tt, small_tex(np.random.default_rng(1))) as r:
+        out = r.render(gel_b200.view_bases([(0, 0)]))
+        assert out["rc"] == gel_b200.GELCU_W_CLIPPED and r.stats()["flags"] & 2
+
+
+def test_batches_read_frame_and_mesh_replacement(cfg1):
+    tv, tn, tt, tex = cfg1
+    bases = gel_b200.view_bases([(0.1 * k, 0.02 * k) for k in range(10)])
+    with make_renderer(800, 600, tv, tn, tt, tex) as r:
+        r.set_option("batch_views", 3)
+        out, ref = assert_views_match(r, tv, tn, tt, tex, bases)
+        assert r.stats()["batches"] == 4
+        r.render(bases, pixels=False)                      # frames stay on the device
+        px, zb = r.read_frame(0)                           # slot 0 of the last batch = view 9
+        assert np.array_equal(px, ref["pixel"][9]) and np.array_equal(bits(zb), bits(ref["z"][9]))
+        rng = np.random.default_rng(2)
+        tv2, tn2, tt2 = random_soup(rng, 100)
+        r.set_mesh(tv2, tn2, tt2)
+        assert_views_match(r, tv2, tn2, tt2, tex, bases[:2])
+
+
+def test_call_order_and_argument_errors():
+    r = gel_b200.Renderer(64, 64)
+    with pytest.raises(gel_b200.GelcuError) as e:
+        r.render(gel_b200.view_bases([(0, 0)]))
+    assert e.value.code == gel_b200.GELCU_E_INVALID
+    with pytest.raises(gel_b200.GelcuError):
+        r.set_option("no_such_option", 1)
+    r.close()
+    with pytest.raises(gel_b200.GelcuError):
+        gel_b200.Renderer(0, 10)
+    with pytest.raises(gel_b200.GelcuError):
+        gel_b200.Renderer(64, 64, device=99)
+
+
+def test_headless_gel_matches_reference_output_format(cfg1_paths, golden):
+    """The host C program end to end: same per-frame FNV / non-zero lines as the unmodified reference printed."""
+    import json, subprocess
+    from conftest import ROOT
+    case = golden["cases"][1]                              # 800x600, mouse (-37, 11), 4 frames
+    exe = os.path.join(ROOT, "gel_b200", "host", "gel")
+    out = subprocess.run([exe, *cfg1_paths, "--frames", "4", "--mouse", "-37,11"], capture_output=True, text=True, check=True).stdout
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    for f, l in zip(case["frames"], lines):
+        assert l["fnv"] == f["fnv"] and l["nonzero"] == f["nonzero"] and l["checksum"] == f["salted_sum"]
+    assert lines[-1]["summary"] and lines[-1]["views"] == 4

@@ -1,0 +1,136 @@
+"""The product's host C flow (gel_b200/host/gel_host.c) against the oracle's restatement of main.c:84-180, 227-286,
+471-484, 506-512 -- and the ABI surface of libgelcu.so (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import gel_b200
+import oracle
+from conftest import ROOT, bits
+
+
+def test_obj_and_bmp_loaders_match_oracle(cfg1_paths):
+    tv, tn, tt = gel_b200.load_obj(cfg1_paths[0])
+    otv, otn, ott = oracle.load_obj(cfg1_paths[0])
+    assert tv.shape == (5000, 9)
+    for a, b in ((tv, otv), (tn, otn), (tt, ott)):
+        assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(gel_b200.load_bmp(cfg1_paths[1]), oracle.load_bmp(cfg1_paths[1]))
+
+
+def test_obj_grammar_quirks(tmp_path):
+    """Dispatch order vn / vt / v / f, 1-based indices, int-truncated scale (main.c:244): max|v| = 2.9 -> scale 2."""
+    p = tmp_path / "q.obj"
+    p.write_text("# comment\n\nvn 0 0 1\nvn 0 1 0\nvt 0.25 0.75 0\nvt 1 0 0\nvt 0 1 0\n"
+                 "v 2.9 0 0\nv 0 1.5 0\nv 0 0 -1\nv 0.5 0.5 0.5\ng group\ns off\n"
+                 "f 1/1/1 2/2/2 3/3/1\nf 4/3/2 3/2/1 2/1/1 1/1/1\n")
+    tv, tn, tt = gel_b200.load_obj(str(p))
+    otv, otn, ott = oracle.load_obj(str(p))
+    assert tv.shape == (2, 9)
+    assert np.array_equal(bits(tv), bits(otv)) and np.array_equal(bits(tn), bits(otn)) and np.array_equal(bits(tt), bits(ott))
+    assert tv[0, 0] == np.float32(2.9) * np.float32(0.5)
+    assert list(tt[1, :3]) == [0.0, 1.0, 0.0] and list(tn[1, :3]) == [0.0, 1.0, 0.0]
+
+
+def test_obj_errors(tmp_path):
+    with pytest.raises(RuntimeError):
+        gel_b200.load_obj(str(tmp_path / "missing.obj"))
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 1 0 0\nvt 0 0 0\nvn 0 0 1\nf 1/1/1 2/1/1 1/1/1\n")       # index 2 out of range
+    with pytest.raises(RuntimeError):
+        gel_b200.load_obj(str(bad))
+    small = tmp_path / "small.obj"
+    small.write_text("v 0.5 0 0\nvt 0 0 0\nvn 0 0 1\nf 1/1/1 1/1/1 1/1/1\n")   # (int)maxlen == 0 (Q5)
+    with pytest.raises(RuntimeError):
+        gel_b200.load_obj(str(small))
+
+
+def test_bmp_padding_and_topdown(tmp_path):
+    import struct
+    w, h = 3, 2                                  # row = 9 bytes + 3 pad
+    rows = [bytes([10 * y + x for x in range(9)]) + b"\0\0\0" for y in range(h)]
+    for sign in (1, -1):
+        hdr = struct.pack("<2sIHHI", b"BM", 54 + 24, 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, sign * h, 1, 24, 0, 24, 0, 0, 0, 0)
+        p = tmp_path / f"t{sign}.bmp"
+        p.write_bytes(hdr + b"".join(rows))
+        t = gel_b200.load_bmp(str(p))
+        assert np.array_equal(t, oracle.load_bmp(str(p)))
+        file_row0 = [(2 << 16) | (1 << 8) | 0, (5 << 16) | (4 << 8) | 3, (8 << 16) | (7 << 8) | 6]
+        assert list(t[h - 1 if sign == 1 else 0]) == file_row0
+    with pytest.raises(RuntimeError):
+        gel_b200.load_bmp(str(tmp_path / "nope.bmp"))
+
+
+def test_view_basis_matches_oracle_bitwise():
+    rng = np.random.default_rng(7)
+    for xt, yt in [(0, 0), (0.2, 0), (np.pi, 0.1), (-1.3, 0.7)] + list(rng.uniform(-7, 7, (200, 2))):
+        assert np.array_equal(bits(gel_b200.view_basis(xt, yt)), bits(oracle.view_basis(xt, yt)))
+    b = gel_b200.view_basis(0, 0)
+    assert list(b) == [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1]
+
+
+def test_input_step_matches_reference_accumulation():
+    xt, yt = ctypes.c_float(0), ctypes.c_float(0)
+    ang = oracle.mouse_angles(50, -37, 11)
+    for k in range(50):
+        assert (np.float32(xt.value), np.float32(yt.value)) == (ang[k, 0], ang[k, 1])
+        gel_b200.host().gel_input_step(ctypes.byref(xt), ctypes.byref(yt), -37, 11)
+
+
+def test_fnv_and_upright(cfg1):
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 2**32, 1000, dtype=np.uint32)
+    assert gel_b200.fnv1a64_words(w) == oracle.fnv1a64_words(w)
+    xres, yres = 5, 3
+    canvas = np.arange(xres * yres, dtype=np.uint32)
+    up = np.zeros(xres * yres, np.uint32)
+    gel_b200.host().gel_upright(canvas.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), xres, yres, up.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    for wy in range(yres):
+        for wx in range(xres):
+            assert up[wy * xres + wx] == canvas[(yres - 1 - wy) + wx * yres]
+
+
+def test_abi_exports_every_declared_symbol():
+    """libgelcu.so loads without a GPU and exports exactly the entry points include/gelcu.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "gelcu.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|void|const char\*)\s+(gelcu_[a-z_]+)\s*\(", hdr, re.M)))
+    assert declared == sorted(gel_b200.GELCU_SYMBOLS)
+    L = gel_b200.cu()
+    for s in declared:
+        assert hasattr(L, s), s
+    nm = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "gel_b200", "libgelcu.so")], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (gelcu_[a-z_]+)", nm)))
+    assert exported == declared
+
+
+def test_no_gpu_fails_loudly():
+    """No CPU fallback: without a device, context creation reports GELCU_E_NOGPU (skipped where a GPU exists)."""
+    L = gel_b200.cu()
+    if L.gelcu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(gel_b200.GelcuError) as e:
+        gel_b200.Renderer(800, 600)
+    assert e.value.code == gel_b200.GELCU_E_NOGPU and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under gel_b200/ or include/ may import, link or open oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "gel_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cpp")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "geloracle" not in text and "ref_cpu" not in text, f
+    ldd = subprocess.run(["ldd", os.path.join(ROOT, "gel_b200", "libgelcu.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+
+
+def test_headless_gel_usage_and_errors(tmp_path):
+    exe = os.path.join(ROOT, "gel_b200", "host", "gel")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("args: path/to/obj path/to/bmp")      # main.c:488-492
+    r = subprocess.run([exe, str(tmp_path / "none.obj"), str(tmp_path / "none.bmp")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("could not open")                      # main.c:463-467
