@@ -1,0 +1,538 @@
+/* gel_kernels.cuh -- the three sm_100a kernels of gel's per-frame render path (device code only).
+ *
+ *   K1 transform_kernel   one thread per (view, distinct corner): tviewnrm / tviewtri / tperspective / tviewport
+ *                         (main.c:372-390, 302-314, 288-300); float4 in, float4 (screen x, y, z, shade) out
+ *   K2 bin_kernel         triangle setup + screen-tile binning in ONE pass: a CTA takes 1024 consecutive
+ *                         triangles, computes each bbox (main.c:344-347), groups the (triangle, tile) pairs by
+ *                         tile in shared memory (count -> scan -> place) and publishes one SEGMENT per touched
+ *                         tile: a contiguous run of entries in a per-view pool, pushed on the tile's chain
+ *   K3 raster_kernel      persistent CTAs pull (view, tile) items; the tile's depth + winner live in shared
+ *                         memory as one 64-bit key per pixel.  Small triangles are expanded into FRAGMENTS
+ *                         (one lane per bbox pixel, so lanes stay busy whatever the triangle sizes); large ones
+ *                         are swept by the whole CTA with every pixel owned by one thread.  The winning fragment
+ *                         of each pixel is shaded once (main.c:358-366) and the tile goes back to HBM in one
+ *                         coalesced pass.
+ *
+ * Draw-order semantics (main.c:356: strict `z > zbuff`, so the FIRST submitted triangle wins a tie) are kept
+ * exactly by resolving  key = zkey(z) << 32 | (0xFFFFFFFF - triangle_index)  with a 64-bit max:
+ * "first triangle in submission order to reach a strictly greater z" == "greatest z, ties to the lowest index".
+ * The result therefore does not depend on the order in which a tile's triangles are visited.
+ */
+#ifndef GEL_KERNELS_CUH
+#define GEL_KERNELS_CUH
+
+#include "../../include/gelcu.h"
+#include "gel_math.h"
+
+#include <cuda_runtime.h>
+
+namespace gelk {
+
+constexpr int TW = 32;             /* tile width  (screen x, the framebuffer's SLOW axis)                */
+constexpr int TH = 32;             /* tile height (screen y, contiguous in memory: index y + x*yres)     */
+constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+constexpr int FRAG_MAX = 128;      /* bbox-in-tile pixels up to which a triangle is expanded into fragments */
+constexpr int WINDOW = 1024;       /* fragments staged per warp per pass                                  */
+constexpr int SEG_SLOTS = 256;     /* segments staged per round (one per thread)                          */
+constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_TPT = 4;         /* triangles per thread in K2                                          */
+constexpr int BIN_CHUNK = BIN_THREADS * BIN_TPT;
+constexpr int LOCAL_MAX = 1024;    /* tile slots a K2 CTA can group locally                               */
+constexpr int HUGE_TILES = 16;     /* triangles covering more tiles than this are published tile by tile  */
+constexpr unsigned long long CLEAR_KEY = (0x00800000ull << 32) | 0xFFFFFFFFull;   /* zkey(-FLT_MAX), no winner */
+constexpr uint32_t FLAG_CLIPPED = 1u, FLAG_TEXCLAMP = 2u, FLAG_OVERFLOW = 0x80000000u;
+constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K1: vertex transform                                                                             */
+/* ------------------------------------------------------------------------------------------------ */
+
+__global__ void __launch_bounds__(256)
+transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict__ vpos,
+                 const float4* __restrict__ vnrm, float4* __restrict__ xf, int nuniq, int xres, int yres)
+{
+    const int view = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nuniq) return;
+    const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
+    const float4 p = __ldg(vpos + i);
+    const float4 n = __ldg(vnrm + i);
+    float4 o;
+    gel::transform_corner(c, p.x, p.y, p.z, n.x, n.y, n.z, o.x, o.y, o.z, o.w);
+    xf[(size_t) view * nuniq + i] = o;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K2: setup + binning                                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct BinParams
+{
+    const float4* xf; const uint32_t *i0, *i1, *i2;
+    uint4* entries;      /* [view][cap_e]   (i0, i1, i2, triangle)                                        */
+    uint4* descs;        /* [view][cap_d]   (next desc or -1, first entry, entry count, chunk)            */
+    int* heads;          /* [view][ntiles][NCHAIN]  top of each chain, -1 = empty                         */
+    int* cursors;        /* [view][2]       entries used, descs used (keep counting past the capacity)    */
+    uint32_t* flags;     /* [view]                                                                        */
+    int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d;
+};
+
+__device__ __forceinline__ void publish_segment(const BinParams& p, int view, int tile, int chunk, int id, int first, int count)
+{
+    int* head = p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + (chunk % NCHAIN);
+    const int prev = atomicExch(head, id);
+    p.descs[(size_t) view * p.cap_d + id] = make_uint4((uint32_t) prev, (uint32_t) first, (uint32_t) count, (uint32_t) chunk);
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_kernel(BinParams p)
+{
+    __shared__ int s_cnt[LOCAL_MAX];     /* pairs per local tile slot                         */
+    __shared__ int s_pre[LOCAL_MAX];     /* exclusive prefix: entries | segments << 20        */
+    __shared__ int s_fil[LOCAL_MAX];     /* placement cursor per slot                         */
+    __shared__ int s_rect[4];            /* CTA bounding tile rect of its normal triangles    */
+    __shared__ int s_warp[BIN_THREADS / 32];
+    __shared__ int s_ebase, s_dbase, s_ok;
+
+    const int view = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* xf = p.xf + (size_t) view * p.nuniq;
+    if(tid == 0) { s_rect[0] = 1 << 30; s_rect[1] = 1 << 30; s_rect[2] = -1; s_rect[3] = -1; }
+    __syncthreads();
+
+    /* ---- per triangle: bbox (main.c:344-347) -> tile rect ---- */
+    uint32_t vi[BIN_TPT][3];
+    uint32_t rect[BIN_TPT];                /* tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24 (tile coordinates < 256: gelcu_create) */
+    unsigned valid = 0;                    /* bit k: triangle k has something to bin */
+    int minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
+    bool clipped = false;
+    #pragma unroll
+    for(int k = 0; k < BIN_TPT; k++)
+    {
+        const int t = chunk * BIN_CHUNK + k * BIN_THREADS + tid;
+        rect[k] = 0;
+        if(t < p.ntri)
+        {
+            vi[k][0] = __ldg(p.i0 + t); vi[k][1] = __ldg(p.i1 + t); vi[k][2] = __ldg(p.i2 + t);
+            const float4 a = __ldg(xf + vi[k][0]), b = __ldg(xf + vi[k][1]), c = __ldg(xf + vi[k][2]);
+            int x0 = gel::trunc_i(fminf(a.x, fminf(b.x, c.x)));
+            int y0 = gel::trunc_i(fminf(a.y, fminf(b.y, c.y)));
+            int x1 = gel::trunc_i(fmaxf(a.x, fmaxf(b.x, c.x)));
+            int y1 = gel::trunc_i(fmaxf(a.y, fmaxf(b.y, c.y)));
+            if(x0 < 0 || y0 < 0 || x1 > p.xres - 1 || y1 > p.yres - 1)
+            {
+                clipped = true;            /* the reference writes out of bounds here */
+                x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, p.xres - 1); y1 = min(y1, p.yres - 1);
+            }
+            if(x0 <= x1 && y0 <= y1)
+            {
+                const int tx0 = x0 / TW, ty0 = y0 / TH, tx1 = x1 / TW, ty1 = y1 / TH;
+                rect[k] = (uint32_t) tx0 | (uint32_t) ty0 << 8 | (uint32_t) tx1 << 16 | (uint32_t) ty1 << 24;
+                valid |= 1u << k;
+                if((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= HUGE_TILES)
+                { minx = min(minx, tx0); miny = min(miny, ty0); maxx = max(maxx, tx1); maxy = max(maxy, ty1); }
+            }
+        }
+    }
+    if(__any_sync(0xFFFFFFFFu, clipped) && lane == 0) atomicOr(p.flags + view, FLAG_CLIPPED);
+    for(int d = 16; d; d >>= 1)
+    {
+        minx = min(minx, __shfl_xor_sync(0xFFFFFFFFu, minx, d)); miny = min(miny, __shfl_xor_sync(0xFFFFFFFFu, miny, d));
+        maxx = max(maxx, __shfl_xor_sync(0xFFFFFFFFu, maxx, d)); maxy = max(maxy, __shfl_xor_sync(0xFFFFFFFFu, maxy, d));
+    }
+    if(lane == 0 && maxx >= 0) { atomicMin(&s_rect[0], minx); atomicMin(&s_rect[1], miny); atomicMax(&s_rect[2], maxx); atomicMax(&s_rect[3], maxy); }
+    __syncthreads();
+    const int rx0 = s_rect[0], ry0 = s_rect[1];
+    const int RW = s_rect[2] - rx0 + 1, RH = s_rect[3] - ry0 + 1;
+    const int nslots = s_rect[2] >= 0 ? RW * RH : 0;
+    const bool local = nslots > 0 && nslots <= LOCAL_MAX;
+    __syncthreads();
+
+    if(local)
+    {
+        for(int s = tid; s < nslots; s += BIN_THREADS) { s_cnt[s] = 0; s_fil[s] = 0; }
+        __syncthreads();
+        /* count */
+        #pragma unroll
+        for(int k = 0; k < BIN_TPT; k++)
+        {
+            if(!(valid >> k & 1)) continue;
+            const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
+            if((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > HUGE_TILES) continue;
+            for(int tx = tx0; tx <= tx1; tx++)
+                for(int ty = ty0; ty <= ty1; ty++) atomicAdd(&s_cnt[(tx - rx0) * RH + (ty - ry0)], 1);
+        }
+        __syncthreads();
+        /* exclusive scan of (count | nonzero << 20) over the slots, 4 consecutive slots per thread */
+        int v[4], sum = 0;
+        #pragma unroll
+        for(int j = 0; j < 4; j++)
+        {
+            const int s = tid * 4 + j;
+            const int cn = s < nslots ? s_cnt[s] : 0;
+            v[j] = cn | (cn > 0 ? 1 << 20 : 0);
+            sum += v[j];
+        }
+        int incl = sum;
+        for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+        if(lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+        #pragma unroll
+        for(int w = 0; w < BIN_THREADS / 32; w++) { const int x = s_warp[w]; if(w < warp) wbase += x; total += x; }
+        int run = wbase + incl - sum;
+        #pragma unroll
+        for(int j = 0; j < 4; j++) { const int s = tid * 4 + j; if(s < nslots) s_pre[s] = run; run += v[j]; }
+        if(tid == 0)
+        {
+            const int E = total & 0xFFFFF, S = total >> 20;
+            int* cur = p.cursors + 2 * view;
+            const int eb = atomicAdd(cur, E), db = atomicAdd(cur + 1, S);
+            s_ebase = eb; s_dbase = db;
+            s_ok = (eb + E <= p.cap_e && db + S <= p.cap_d) ? 1 : 0;
+            if(!s_ok) atomicOr(p.flags + view, FLAG_OVERFLOW);
+        }
+        __syncthreads();
+        if(s_ok)
+        {
+            uint4* entries = p.entries + (size_t) view * p.cap_e + s_ebase;
+            /* place */
+            #pragma unroll
+            for(int k = 0; k < BIN_TPT; k++)
+            {
+                if(!(valid >> k & 1)) continue;
+                const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
+                if((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > HUGE_TILES) continue;
+                const uint4 ent = make_uint4(vi[k][0], vi[k][1], vi[k][2], (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid));
+                for(int tx = tx0; tx <= tx1; tx++)
+                    for(int ty = ty0; ty <= ty1; ty++)
+                    {
+                        const int s = (tx - rx0) * RH + (ty - ry0);
+                        entries[(s_pre[s] & 0xFFFFF) + atomicAdd(&s_fil[s], 1)] = ent;
+                    }
+            }
+            /* publish one segment per touched tile */
+            for(int s = tid; s < nslots; s += BIN_THREADS)
+            {
+                const int cn = s_cnt[s];
+                if(cn > 0)
+                {
+                    const int tile = (rx0 + s / RH) * p.tiles_y + (ry0 + s % RH);
+                    publish_segment(p, view, tile, chunk, s_dbase + (s_pre[s] >> 20), s_ebase + (s_pre[s] & 0xFFFFF), cn);
+                }
+            }
+        }
+    }
+
+    /* triangles that are huge, or all of them when the CTA's footprint does not fit the local grouping:
+     * one single-entry segment per (triangle, tile) */
+    #pragma unroll
+    for(int k = 0; k < BIN_TPT; k++)
+    {
+        if(!(valid >> k & 1)) continue;
+        const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
+        if(local && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= HUGE_TILES) continue;
+        const uint4 ent = make_uint4(vi[k][0], vi[k][1], vi[k][2], (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid));
+        int* cur = p.cursors + 2 * view;
+        for(int tx = tx0; tx <= tx1; tx++)
+            for(int ty = ty0; ty <= ty1; ty++)
+            {
+                const int e = atomicAdd(cur, 1), id = atomicAdd(cur + 1, 1);
+                if(e < p.cap_e && id < p.cap_d)
+                {
+                    p.entries[(size_t) view * p.cap_e + e] = ent;
+                    publish_segment(p, view, tx * p.tiles_y + ty, chunk, id, e, 1);
+                }
+                else atomicOr(p.flags + view, FLAG_OVERFLOW);
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K3: tile rasteriser                                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct RasterParams
+{
+    const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
+    const uint4* entries; const uint4* descs; const int* heads;
+    const uint32_t* tex; int tw, th;
+    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;
+    int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
+};
+
+struct RasterSmem
+{
+    unsigned long long keys[TW * TH];                 /*  8 KB  depth+winner per pixel, index x_local*TH + y_local  */
+    float4 slab[4][RASTER_THREADS];                   /* 16 KB  per-triangle constants of the current round         */
+    unsigned short owner[RASTER_WARPS][WINDOW];       /* 16 KB  fragment -> (lane << 10 | x_local << 5 | y_local)   */
+    int seg_first[SEG_SLOTS];                         /*  1 KB  */
+    int seg_pre[SEG_SLOTS];                           /*  1 KB  exclusive prefix of segment sizes                   */
+    uint32_t bbox[RASTER_THREADS];                    /*  1 KB  clipped local bbox + flags of the round's triangles */
+    unsigned short large_list[RASTER_THREADS];
+    int chain[NCHAIN];
+    int warp_sums[RASTER_WARPS];
+    unsigned long long hash[2];
+    int item, nlarge, more;
+};
+
+/* slab layout (den-sign normalised: if den < 0 the four Gram terms are negated, which negates both
+ * numerators and the denominator exactly, so the quotients are unchanged):
+ *   q0 = ax, ay, v0x, v0y      q1 = v1x, v1y, k0, k1      q2 = d00, d01, d11, den (> 0)      q3 = az, bz, cz, ~tri */
+__device__ __forceinline__ void numerators(const float4& q0, const float4& q1, const float4& q2, float fx, float fy, float& nv, float& nw)
+{
+    const float v2x = gel::sub(fx, q0.x), v2y = gel::sub(fy, q0.y);
+    const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), gel::mul(v2y, q0.w)), q1.z);
+    const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), gel::mul(v2y, q1.y)), q1.w);
+    nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+    nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+}
+
+/* division, inside test and depth of main.c:327-329, 352, 355; returns the key or 0 when outside */
+__device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, float den, const float4& q3)
+{
+    const float v = gel::dvd(nv, den), w = gel::dvd(nw, den);
+    const float u = gel::sub(gel::sub(1.0f, v), w);
+    if(!(v >= 0.0f && w >= 0.0f && u >= 0.0f)) return 0ull;
+    const float z = gel::add(gel::add(gel::mul(v, q3.y), gel::mul(w, q3.z)), gel::mul(u, q3.x));
+    return ((unsigned long long) gel::zkey(z) << 32) | __float_as_uint(q3.w);
+}
+
+template<bool HASH>
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_kernel(RasterParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RasterSmem& sm = *reinterpret_cast<RasterSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nitems = p.nviews * p.ntiles;
+    const bool vec_ok = (p.yres & 3) == 0;
+    for(;;)
+    {
+        if(tid == 0) { sm.item = atomicAdd(p.work_counter, 1); sm.hash[0] = 0; sm.hash[1] = 0; }
+        __syncthreads();
+        const int item = sm.item;
+        if(item >= nitems) break;
+        const int view = item / p.ntiles, tile = item - view * p.ntiles;
+        const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
+        const int px0 = tx * TW, py0 = ty * TH;
+        const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
+        uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
+        float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
+        const float4* xf = p.xf + (size_t) view * p.nuniq;
+        const uint4* descs = p.descs + (size_t) view * p.cap_d;
+        const uint4* entries = p.entries + (size_t) view * p.cap_e;
+        unsigned long long hp = 0, hz = 0;
+
+        int head = -1;
+        if(tid < NCHAIN) { head = __ldg(p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + tid); sm.chain[tid] = head; }
+        const bool empty = __syncthreads_and(head < 0);
+
+        if(empty)
+        {
+            /* reset (main.c:413-417) for a tile nothing touches: straight to HBM */
+            if(!HASH && vec_ok && py1 - py0 + 1 == TH)
+            {
+                const int x = px0 + (tid >> 3), y = py0 + (tid & 7) * 4;
+                if(x <= px1)
+                {
+                    const size_t idx = (size_t) y + (size_t) x * p.yres;
+                    *reinterpret_cast<uint4*>(pixel + idx) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<float4*>(zbuf + idx) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                }
+            }
+            else
+                for(int i = tid; i < TW * TH; i += RASTER_THREADS)
+                {
+                    const int x = px0 + (i >> 5), y = py0 + (i & 31);
+                    if(x <= px1 && y <= py1)
+                    {
+                        const int idx = y + x * p.yres;
+                        pixel[idx] = 0u;
+                        zbuf[idx] = -FLT_MAX;
+                        if(HASH) { hp += gel::salt_mix(0u, (uint32_t) idx); hz += gel::salt_mix(0xFF7FFFFFu, (uint32_t) idx); }
+                    }
+                }
+        }
+        else
+        {
+            for(int i = tid; i < TW * TH; i += RASTER_THREADS) sm.keys[i] = CLEAR_KEY;
+
+            /* ================= visibility: every (triangle, pixel) of main.c:348-356 inside this tile ================= */
+            for(;;)
+            {
+                /* ---- stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) ---- */
+                sm.seg_first[tid] = 0;
+                int my_count = 0;
+                __syncthreads();
+                if(tid < NCHAIN)
+                {
+                    int cur = sm.chain[tid], k = 0;
+                    while(cur >= 0 && k < SEG_SLOTS / NCHAIN)
+                    {
+                        const uint4 d = __ldg(descs + cur);
+                        sm.seg_first[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.y;
+                        sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.z;      /* size for now */
+                        cur = (int) d.x; k++;
+                    }
+                    for(; k < SEG_SLOTS / NCHAIN; k++) sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = 0;
+                    sm.chain[tid] = cur;
+                }
+                const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
+                /* exclusive scan of the staged segment sizes (one slot per thread) */
+                my_count = sm.seg_pre[tid];
+                int incl = my_count;
+                for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+                if(lane == 31) sm.warp_sums[warp] = incl;
+                __syncthreads();
+                int wbase = 0, round_entries = 0;
+                #pragma unroll
+                for(int w = 0; w < RASTER_WARPS; w++) { const int x = sm.warp_sums[w]; if(w < warp) wbase += x; round_entries += x; }
+                sm.seg_pre[tid] = wbase + incl - my_count;
+                __syncthreads();
+
+                for(int base = 0; base < round_entries; base += RASTER_THREADS)
+                {
+                    if(tid == 0) sm.nlarge = 0;
+                    const int e = base + tid;
+                    const bool have = e < round_entries;
+                    int npx = 0, bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;     /* tile-local clipped bbox */
+                    bool large = false;
+                    if(have)
+                    {
+                        /* which staged segment holds entry e: last slot with seg_pre <= e (8-step binary search) */
+                        int lo = 0;
+                        #pragma unroll
+                        for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
+                        const uint4 ent = __ldg(entries + sm.seg_first[lo] + (e - sm.seg_pre[lo]));
+                        const float4 a = __ldg(xf + ent.x), b = __ldg(xf + ent.y), c = __ldg(xf + ent.z);
+                        const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+                        bx0 = max(s.x0, px0) - px0; bx1 = min(s.x1, px1) - px0;
+                        by0 = max(s.y0, py0) - py0; by1 = min(s.y1, py1) - py0;
+                        const float ad = fabsf(s.den);
+                        const bool drawable = ad > 0.0f;                     /* den == 0 or NaN never passes main.c:352 */
+                        const bool guard = ad <= GUARD_DEN_MAX;
+                        if(bx0 <= bx1 && by0 <= by1 && drawable) npx = (bx1 - bx0 + 1) * (by1 - by0 + 1);
+                        large = npx > FRAG_MAX || (npx > 0 && !guard);
+                        const float sg = s.den < 0.0f ? -1.0f : 1.0f;        /* exact sign flips */
+                        sm.slab[0][tid] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
+                        sm.slab[1][tid] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
+                        sm.slab[2][tid] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
+                        sm.slab[3][tid] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - ent.w));
+                        sm.bbox[tid] = (uint32_t) bx0 | (uint32_t) bx1 << 5 | (uint32_t) by0 << 10 | (uint32_t) by1 << 15 | (guard ? 1u << 20 : 0u);
+                    }
+                    __syncthreads();                                         /* nlarge = 0 and the slab are visible */
+                    if(large) sm.large_list[atomicAdd(&sm.nlarge, 1)] = (unsigned short) tid;
+
+                    /* ---- small triangles: expand to fragments, one lane per bbox pixel ---- */
+                    const int nfr = large ? 0 : npx;
+                    int fincl = nfr;
+                    for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, fincl, d); if(lane >= d) fincl += n; }
+                    const int fstart = fincl - nfr;
+                    const int ftotal = __shfl_sync(0xFFFFFFFFu, fincl, 31);
+                    unsigned short* owner = sm.owner[warp];
+                    int emitted = 0, x = bx0, y = by0;
+                    for(int w0 = 0; w0 < ftotal; w0 += WINDOW)
+                    {
+                        while(emitted < nfr && fstart + emitted < w0 + WINDOW)
+                        {
+                            owner[fstart + emitted - w0] = (unsigned short) (lane << 10 | x << 5 | y);
+                            emitted++;
+                            if(++y > by1) { y = by0; x++; }
+                        }
+                        __syncwarp();
+                        const int n = min(WINDOW, ftotal - w0);
+                        for(int f = lane; f < n; f += 32)
+                        {
+                            const uint32_t o = owner[f];
+                            const int src = (warp << 5) | (int) (o >> 10), xl = (o >> 5) & 31, yl = o & 31;
+                            const float4 q0 = sm.slab[0][src], q1 = sm.slab[1][src], q2 = sm.slab[2][src];
+                            float nv, nw;
+                            numerators(q0, q1, q2, gel::i2f(px0 + xl), gel::i2f(py0 + yl), nv, nw);
+                            if(nv < -GUARD_EPS || nw < -GUARD_EPS) continue;    /* exact: quotient is a negative non-zero float */
+                            const unsigned long long key = fragment_key(nv, nw, q2.w, sm.slab[3][src]);
+                            unsigned long long* k = sm.keys + xl * TH + yl;
+                            if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
+                        }
+                        __syncwarp();
+                    }
+                    __syncthreads();                                         /* large_list complete, fragment atomics done */
+
+                    /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
+                     *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
+                    const int nlarge = sm.nlarge;
+                    for(int li = 0; li < nlarge; li++)
+                    {
+                        const int src = sm.large_list[li];
+                        const uint32_t bb = sm.bbox[src];
+                        const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
+                        if(lane < gy0 || lane > gy1) continue;
+                        const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
+                        const float4 q0 = sm.slab[0][src], q1 = sm.slab[1][src], q2 = sm.slab[2][src], q3 = sm.slab[3][src];
+                        const float fy = gel::i2f(py0 + lane);
+                        for(int xl = gx0 + ((warp - gx0) & (RASTER_WARPS - 1)); xl <= gx1; xl += RASTER_WARPS)
+                        {
+                            float nv, nw;
+                            numerators(q0, q1, q2, gel::i2f(px0 + xl), fy, nv, nw);
+                            if(nv < eps || nw < eps) continue;
+                            const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
+                            unsigned long long* k = sm.keys + xl * TH + lane;
+                            if(key > *k) *k = key;
+                        }
+                    }
+                    __syncthreads();                                         /* slab / bbox / large_list reusable */
+                }
+                if(!more) break;
+            }
+            __syncthreads();
+
+            /* ================= shade the winner of every pixel once (main.c:358-366), write the tile back ================= */
+            for(int i = tid; i < TW * TH; i += RASTER_THREADS)
+            {
+                const int x = px0 + (i >> 5), y = py0 + (i & 31);
+                if(x > px1 || y > py1) continue;
+                const unsigned long long key = sm.keys[i];
+                uint32_t colour = 0u;
+                float z = -FLT_MAX;
+                if(key != CLEAR_KEY)
+                {
+                    const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
+                    z = gel::zkey_inv((uint32_t) (key >> 32));
+                    const float4 a = __ldg(xf + __ldg(p.i0 + tri));
+                    const float4 b = __ldg(xf + __ldg(p.i1 + tri));
+                    const float4 c = __ldg(xf + __ldg(p.i2 + tri));
+                    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+                    float nv, nw, v, w, u, zz;
+                    gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+                    gel::bary_inside(s, nv, nw, v, w, u, zz);
+                    const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
+                    const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
+                    int xx, yy, shading;
+                    gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
+                    if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
+                    {
+                        atomicOr(p.flags + view, FLAG_TEXCLAMP);   /* the reference reads out of bounds here (R) */
+                        xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
+                    }
+                    colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+                }
+                const int idx = y + x * p.yres;
+                pixel[idx] = colour;
+                zbuf[idx] = z;
+                if(HASH) { hp += gel::salt_mix(colour, (uint32_t) idx); hz += gel::salt_mix(__float_as_uint(z), (uint32_t) idx); }
+            }
+        }
+        if(HASH)
+        {
+            for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+            if(lane == 0) { atomicAdd(&sm.hash[0], hp); atomicAdd(&sm.hash[1], hz); }
+            __syncthreads();
+            if(tid == 0) { atomicAdd(p.hash + 2 * view, sm.hash[0]); atomicAdd(p.hash + 2 * view + 1, sm.hash[1]); }
+        }
+        __syncthreads();
+    }
+}
+
+} /* namespace gelk */
+#endif /* GEL_KERNELS_CUH */
