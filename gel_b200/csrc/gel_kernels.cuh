@@ -32,8 +32,11 @@ constexpr int TW = 32;             /* tile width  (screen x, the framebuffer's S
 constexpr int TH = 32;             /* tile height (screen y, contiguous in memory: index y + x*yres)     */
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int FRAG_MAX = 128;      /* bbox-in-tile pixels up to which a triangle is expanded into fragments */
-constexpr int WINDOW = 1024;       /* fragments staged per warp per pass                                  */
+constexpr int FRAG_MAX = 256;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
+constexpr int ROWS = 4;            /* rows per column unit                                                */
+constexpr int UNIT_WINDOW = 512;   /* column units staged per warp per pass                               */
+constexpr int QCAP = 160;          /* survivor stack per warp: < 32 left over + 32 lanes x ROWS           */
+constexpr int DEFER_MAX = 1024;    /* large triangles per round left to the CTA-wide sweep                */
 constexpr int SEG_SLOTS = 256;     /* segments staged per round (one per thread)                          */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
 constexpr int BIN_THREADS = 256;
@@ -71,7 +74,7 @@ transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict_
 struct BinParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2;
-    uint4* entries;      /* [view][cap_e]   (i0, i1, i2, triangle)                                        */
+    uint32_t* entries;   /* [view][cap_e]   triangle index                                                */
     uint4* descs;        /* [view][cap_d]   (next desc or -1, first entry, entry count, chunk)            */
     int* heads;          /* [view][ntiles][NCHAIN]  top of each chain, -1 = empty                         */
     int* cursors;        /* [view][2]       entries used, descs used (keep counting past the capacity)    */
@@ -102,7 +105,6 @@ bin_kernel(BinParams p)
     __syncthreads();
 
     /* ---- per triangle: bbox (main.c:344-347) -> tile rect ---- */
-    uint32_t vi[BIN_TPT][3];
     uint32_t rect[BIN_TPT];                /* tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24 (tile coordinates < 256: gelcu_create) */
     unsigned valid = 0;                    /* bit k: triangle k has something to bin */
     int minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
@@ -114,8 +116,7 @@ bin_kernel(BinParams p)
         rect[k] = 0;
         if(t < p.ntri)
         {
-            vi[k][0] = __ldg(p.i0 + t); vi[k][1] = __ldg(p.i1 + t); vi[k][2] = __ldg(p.i2 + t);
-            const float4 a = __ldg(xf + vi[k][0]), b = __ldg(xf + vi[k][1]), c = __ldg(xf + vi[k][2]);
+            const float4 a = __ldg(xf + __ldg(p.i0 + t)), b = __ldg(xf + __ldg(p.i1 + t)), c = __ldg(xf + __ldg(p.i2 + t));
             int x0 = gel::trunc_i(fminf(a.x, fminf(b.x, c.x)));
             int y0 = gel::trunc_i(fminf(a.y, fminf(b.y, c.y)));
             int x1 = gel::trunc_i(fmaxf(a.x, fmaxf(b.x, c.x)));
@@ -196,7 +197,7 @@ bin_kernel(BinParams p)
         __syncthreads();
         if(s_ok)
         {
-            uint4* entries = p.entries + (size_t) view * p.cap_e + s_ebase;
+            uint32_t* entries = p.entries + (size_t) view * p.cap_e + s_ebase;
             /* place */
             #pragma unroll
             for(int k = 0; k < BIN_TPT; k++)
@@ -204,7 +205,7 @@ bin_kernel(BinParams p)
                 if(!(valid >> k & 1)) continue;
                 const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
                 if((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > HUGE_TILES) continue;
-                const uint4 ent = make_uint4(vi[k][0], vi[k][1], vi[k][2], (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid));
+                const uint32_t ent = (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid);
                 for(int tx = tx0; tx <= tx1; tx++)
                     for(int ty = ty0; ty <= ty1; ty++)
                     {
@@ -233,7 +234,7 @@ bin_kernel(BinParams p)
         if(!(valid >> k & 1)) continue;
         const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
         if(local && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= HUGE_TILES) continue;
-        const uint4 ent = make_uint4(vi[k][0], vi[k][1], vi[k][2], (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid));
+        const uint32_t ent = (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid);
         int* cur = p.cursors + 2 * view;
         for(int tx = tx0; tx <= tx1; tx++)
             for(int ty = ty0; ty <= ty1; ty++)
@@ -256,40 +257,63 @@ bin_kernel(BinParams p)
 struct RasterParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
-    const uint4* entries; const uint4* descs; const int* heads;
+    const uint32_t* entries; const uint4* descs; const int* heads;
     const uint32_t* tex; int tw, th;
     uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
 };
 
+/* per-warp scratch of the small-triangle path */
+struct WarpScratch
+{
+    float4 slab[4][32];                 /* 2 KB    per-triangle constants of the warp's current 32 entries          */
+    unsigned short unit[UNIT_WINDOW];   /* 1 KB    column unit -> (lane << 10 | x_local << 5 | first row)           */
+    float q_nv[QCAP], q_nw[QCAP];       /* 1.25 KB survivors of the sign test, waiting for the division stage       */
+    unsigned short q_id[QCAP];          /*         (lane << 10 | x_local << 5 | y_local)                            */
+    uint32_t bbox[32];                  /* clipped tile-local bbox: x0 | x1 << 5 | y0 << 10 | y1 << 15 | guard << 20 */
+};
+
 struct RasterSmem
 {
-    unsigned long long keys[TW * TH];                 /*  8 KB  depth+winner per pixel, index x_local*TH + y_local  */
-    float4 slab[4][RASTER_THREADS];                   /* 16 KB  per-triangle constants of the current round         */
-    unsigned short owner[RASTER_WARPS][WINDOW];       /* 16 KB  fragment -> (lane << 10 | x_local << 5 | y_local)   */
-    int seg_first[SEG_SLOTS];                         /*  1 KB  */
-    int seg_pre[SEG_SLOTS];                           /*  1 KB  exclusive prefix of segment sizes                   */
-    uint32_t bbox[RASTER_THREADS];                    /*  1 KB  clipped local bbox + flags of the round's triangles */
-    unsigned short large_list[RASTER_THREADS];
+    unsigned long long keys[TW * TH];   /* 8 KB  depth+winner per pixel, index x_local*TH + y_local */
+    WarpScratch ws[RASTER_WARPS];
+    int seg_first[SEG_SLOTS];
+    int seg_pre[SEG_SLOTS];             /* exclusive prefix of the staged segment sizes */
+    int defer[DEFER_MAX];               /* entry-pool indices of triangles left to the CTA-wide sweep */
     int chain[NCHAIN];
     int warp_sums[RASTER_WARPS];
     unsigned long long hash[2];
-    int item, nlarge, more;
+    int item, next_entry, ndefer;
 };
 
 /* slab layout (den-sign normalised: if den < 0 the four Gram terms are negated, which negates both
  * numerators and the denominator exactly, so the quotients are unchanged):
  *   q0 = ax, ay, v0x, v0y      q1 = v1x, v1y, k0, k1      q2 = d00, d01, d11, den (> 0)      q3 = az, bz, cz, ~tri */
-__device__ __forceinline__ void numerators(const float4& q0, const float4& q1, const float4& q2, float fx, float fy, float& nv, float& nw)
+struct TriRecord { float4 q0, q1, q2, q3; uint32_t bbox; int npx; };
+
+/* loads triangle `tri` of the view, runs the per-triangle part of tbarycenter/tdraw (main.c:319-324, 344-347)
+ * and clips its bbox to the tile */
+__device__ __forceinline__ TriRecord make_record(const RasterParams& p, const float4* xf, uint32_t tri, int px0, int py0, int px1, int py1)
 {
-    const float v2x = gel::sub(fx, q0.x), v2y = gel::sub(fy, q0.y);
-    const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), gel::mul(v2y, q0.w)), q1.z);
-    const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), gel::mul(v2y, q1.y)), q1.w);
-    nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
-    nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+    const float4 a = __ldg(xf + __ldg(p.i0 + tri)), b = __ldg(xf + __ldg(p.i1 + tri)), c = __ldg(xf + __ldg(p.i2 + tri));
+    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+    const int bx0 = max(s.x0, px0) - px0, bx1 = min(s.x1, px1) - px0;
+    const int by0 = max(s.y0, py0) - py0, by1 = min(s.y1, py1) - py0;
+    const float ad = fabsf(s.den);
+    const bool drawable = ad > 0.0f;                      /* den == 0 or NaN can never pass main.c:352 */
+    const bool guard = ad <= GUARD_DEN_MAX;
+    const float sg = s.den < 0.0f ? -1.0f : 1.0f;         /* exact sign flips */
+    TriRecord r;
+    r.npx = (bx0 <= bx1 && by0 <= by1 && drawable) ? (bx1 - bx0 + 1) * (by1 - by0 + 1) : 0;
+    r.q0 = make_float4(s.ax, s.ay, s.v0x, s.v0y);
+    r.q1 = make_float4(s.v1x, s.v1y, s.k0, s.k1);
+    r.q2 = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
+    r.q3 = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
+    r.bbox = (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15 | (guard ? 1u << 20 : 0u);
+    return r;
 }
 
-/* division, inside test and depth of main.c:327-329, 352, 355; returns the key or 0 when outside */
+/* division, inside test and depth of main.c:327-329, 352, 355; returns the key, or 0 when outside */
 __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, float den, const float4& q3)
 {
     const float v = gel::dvd(nv, den), w = gel::dvd(nw, den);
@@ -299,13 +323,25 @@ __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, f
     return ((unsigned long long) gel::zkey(z) << 32) | __float_as_uint(q3.w);
 }
 
+/* stage 2 of the small path: one survivor per lane */
+__device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws, int i)
+{
+    const uint32_t id = ws.q_id[i];
+    const int src = id >> 10, xl = (id >> 5) & 31, yl = id & 31;
+    const unsigned long long key = fragment_key(ws.q_nv[i], ws.q_nw[i], ws.slab[2][src].w, ws.slab[3][src]);
+    unsigned long long* k = sm.keys + xl * TH + yl;
+    if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
+}
+
 template<bool HASH>
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, 4)
 raster_kernel(RasterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& sm = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpScratch& ws = sm.ws[warp];
     const int nitems = p.nviews * p.ntiles;
     const bool vec_ok = (p.yres & 3) == 0;
     for(;;)
@@ -322,7 +358,7 @@ raster_kernel(RasterParams p)
         float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
         const float4* xf = p.xf + (size_t) view * p.nuniq;
         const uint4* descs = p.descs + (size_t) view * p.cap_d;
-        const uint4* entries = p.entries + (size_t) view * p.cap_e;
+        const uint32_t* entries = p.entries + (size_t) view * p.cap_e;
         unsigned long long hp = 0, hz = 0;
 
         int head = -1;
@@ -363,8 +399,7 @@ raster_kernel(RasterParams p)
             for(;;)
             {
                 /* ---- stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) ---- */
-                sm.seg_first[tid] = 0;
-                int my_count = 0;
+                if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
                 __syncthreads();
                 if(tid < NCHAIN)
                 {
@@ -380,8 +415,7 @@ raster_kernel(RasterParams p)
                     sm.chain[tid] = cur;
                 }
                 const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
-                /* exclusive scan of the staged segment sizes (one slot per thread) */
-                my_count = sm.seg_pre[tid];
+                const int my_count = sm.seg_pre[tid];
                 int incl = my_count;
                 for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
                 if(lane == 31) sm.warp_sums[warp] = incl;
@@ -392,96 +426,138 @@ raster_kernel(RasterParams p)
                 sm.seg_pre[tid] = wbase + incl - my_count;
                 __syncthreads();
 
-                for(int base = 0; base < round_entries; base += RASTER_THREADS)
+                /* ---- small triangles: every warp pulls 32 entries at a time, no CTA barrier inside ---- */
+                int qn = 0;                                                   /* survivors on the warp's stack (warp-uniform) */
+                for(;;)
                 {
-                    if(tid == 0) sm.nlarge = 0;
-                    const int e = base + tid;
-                    const bool have = e < round_entries;
-                    int npx = 0, bx0 = 0, by0 = 0, bx1 = -1, by1 = -1;     /* tile-local clipped bbox */
-                    bool large = false;
-                    if(have)
+                    int e0 = 0;
+                    if(lane == 0) e0 = atomicAdd(&sm.next_entry, 32);
+                    e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+                    if(e0 >= round_entries) break;
+                    const int e = e0 + lane;
+                    int nun = 0, bx0 = 0, by0 = 0, by1 = -1;
+                    if(e < round_entries)
                     {
-                        /* which staged segment holds entry e: last slot with seg_pre <= e (8-step binary search) */
+                        /* staged segment holding entry e: last slot with seg_pre <= e */
                         int lo = 0;
                         #pragma unroll
                         for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
-                        const uint4 ent = __ldg(entries + sm.seg_first[lo] + (e - sm.seg_pre[lo]));
-                        const float4 a = __ldg(xf + ent.x), b = __ldg(xf + ent.y), c = __ldg(xf + ent.z);
-                        const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
-                        bx0 = max(s.x0, px0) - px0; bx1 = min(s.x1, px1) - px0;
-                        by0 = max(s.y0, py0) - py0; by1 = min(s.y1, py1) - py0;
-                        const float ad = fabsf(s.den);
-                        const bool drawable = ad > 0.0f;                     /* den == 0 or NaN never passes main.c:352 */
-                        const bool guard = ad <= GUARD_DEN_MAX;
-                        if(bx0 <= bx1 && by0 <= by1 && drawable) npx = (bx1 - bx0 + 1) * (by1 - by0 + 1);
-                        large = npx > FRAG_MAX || (npx > 0 && !guard);
-                        const float sg = s.den < 0.0f ? -1.0f : 1.0f;        /* exact sign flips */
-                        sm.slab[0][tid] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
-                        sm.slab[1][tid] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
-                        sm.slab[2][tid] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
-                        sm.slab[3][tid] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - ent.w));
-                        sm.bbox[tid] = (uint32_t) bx0 | (uint32_t) bx1 << 5 | (uint32_t) by0 << 10 | (uint32_t) by1 << 15 | (guard ? 1u << 20 : 0u);
-                    }
-                    __syncthreads();                                         /* nlarge = 0 and the slab are visible */
-                    if(large) sm.large_list[atomicAdd(&sm.nlarge, 1)] = (unsigned short) tid;
-
-                    /* ---- small triangles: expand to fragments, one lane per bbox pixel ---- */
-                    const int nfr = large ? 0 : npx;
-                    int fincl = nfr;
-                    for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, fincl, d); if(lane >= d) fincl += n; }
-                    const int fstart = fincl - nfr;
-                    const int ftotal = __shfl_sync(0xFFFFFFFFu, fincl, 31);
-                    unsigned short* owner = sm.owner[warp];
-                    int emitted = 0, x = bx0, y = by0;
-                    for(int w0 = 0; w0 < ftotal; w0 += WINDOW)
-                    {
-                        while(emitted < nfr && fstart + emitted < w0 + WINDOW)
+                        const int pool = sm.seg_first[lo] + (e - sm.seg_pre[lo]);
+                        const TriRecord r = make_record(p, xf, __ldg(entries + pool), px0, py0, px1, py1);
+                        bool unitised = r.npx > 0;
+                        if(r.npx > FRAG_MAX)
                         {
-                            owner[fstart + emitted - w0] = (unsigned short) (lane << 10 | x << 5 | y);
+                            const int slot = atomicAdd(&sm.ndefer, 1);
+                            if(slot < DEFER_MAX) { sm.defer[slot] = pool; unitised = false; }
+                        }
+                        if(unitised)
+                        {
+                            bx0 = r.bbox & 31; by0 = (r.bbox >> 10) & 31; by1 = (r.bbox >> 15) & 31;
+                            const int bx1 = (r.bbox >> 5) & 31;
+                            nun = (bx1 - bx0 + 1) * ((by1 - by0 + ROWS) / ROWS);
+                            ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
+                            ws.bbox[lane] = r.bbox;
+                        }
+                    }
+                    int uincl = nun;
+                    for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
+                    const int ustart = uincl - nun;
+                    const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
+                    int emitted = 0, x = bx0, yb = by0;
+                    __syncwarp();
+                    for(int w0 = 0; w0 < utotal; w0 += UNIT_WINDOW)
+                    {
+                        /* expansion: one 16-bit word per column unit (a column of the bbox, at most ROWS rows) */
+                        while(emitted < nun && ustart + emitted < w0 + UNIT_WINDOW)
+                        {
+                            ws.unit[ustart + emitted - w0] = (unsigned short) (lane << 10 | x << 5 | yb);
                             emitted++;
-                            if(++y > by1) { y = by0; x++; }
+                            yb += ROWS;
+                            if(yb > by1) { yb = by0; x++; }
                         }
                         __syncwarp();
-                        const int n = min(WINDOW, ftotal - w0);
-                        for(int f = lane; f < n; f += 32)
+                        const int n = min(UNIT_WINDOW, utotal - w0);
+                        for(int u0 = 0; u0 < n; u0 += 32)
                         {
-                            const uint32_t o = owner[f];
-                            const int src = (warp << 5) | (int) (o >> 10), xl = (o >> 5) & 31, yl = o & 31;
-                            const float4 q0 = sm.slab[0][src], q1 = sm.slab[1][src], q2 = sm.slab[2][src];
-                            float nv, nw;
-                            numerators(q0, q1, q2, gel::i2f(px0 + xl), gel::i2f(py0 + yl), nv, nw);
-                            if(nv < -GUARD_EPS || nw < -GUARD_EPS) continue;    /* exact: quotient is a negative non-zero float */
-                            const unsigned long long key = fragment_key(nv, nw, q2.w, sm.slab[3][src]);
-                            unsigned long long* k = sm.keys + xl * TH + yl;
-                            if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
+                            /* stage 1: numerators of v and w (main.c:325-328) for the unit's rows; exact sign early-out */
+                            const bool act = u0 + lane < n;
+                            const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
+                            const int src = o >> 10, xl = (o >> 5) & 31, y0l = o & 31;
+                            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
+                            const uint32_t bb = ws.bbox[src];
+                            const int rows = act ? min(ROWS, (int) ((bb >> 15) & 31) - y0l + 1) : 0;
+                            const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
+                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                            const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
+                            #pragma unroll
+                            for(int r = 0; r < ROWS; r++)
+                            {
+                                const float v2y = gel::sub(gel::i2f(py0 + y0l + r), q0.y);
+                                const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
+                                const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
+                                const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                                const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                                /* nv < eps: the quotient nv/den is a negative NON-ZERO float, so main.c:352 fails */
+                                const bool pass = r < rows && !(nv < eps) && !(nw < eps);
+                                const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                                if(pass)
+                                {
+                                    const int slot = qn + __popc(m & lt_mask);
+                                    ws.q_id[slot] = (unsigned short) (src << 10 | xl << 5 | (y0l + r));
+                                    ws.q_nv[slot] = nv; ws.q_nw[slot] = nw;
+                                }
+                                qn += __popc(m);
+                            }
+                            __syncwarp();
+                            /* stage 2: divisions, inside test, depth, key -- full warps off the top of the stack */
+                            while(qn >= 32) { qn -= 32; resolve_survivor(sm, ws, qn + lane); }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                    __syncthreads();                                         /* large_list complete, fragment atomics done */
+                    if(lane < qn) resolve_survivor(sm, ws, lane);
+                    qn = 0;
+                    __syncwarp();
+                }
+                __syncthreads();
 
-                    /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
-                     *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
-                    const int nlarge = sm.nlarge;
-                    for(int li = 0; li < nlarge; li++)
+                /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
+                 *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
+                const int ndefer = min(sm.ndefer, DEFER_MAX);
+                for(int base = 0; base < ndefer; base += RASTER_THREADS)
+                {
+                    if(base + tid < ndefer)
                     {
-                        const int src = sm.large_list[li];
-                        const uint32_t bb = sm.bbox[src];
+                        const TriRecord r = make_record(p, xf, __ldg(entries + sm.defer[base + tid]), px0, py0, px1, py1);
+                        ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
+                        ws.bbox[lane] = r.bbox;
+                    }
+                    __syncthreads();
+                    const int cnt = min(RASTER_THREADS, ndefer - base);
+                    for(int li = 0; li < cnt; li++)
+                    {
+                        const WarpScratch& os = sm.ws[li >> 5];
+                        const int src = li & 31;
+                        const uint32_t bb = os.bbox[src];
                         const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
                         if(lane < gy0 || lane > gy1) continue;
                         const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                        const float4 q0 = sm.slab[0][src], q1 = sm.slab[1][src], q2 = sm.slab[2][src], q3 = sm.slab[3][src];
-                        const float fy = gel::i2f(py0 + lane);
+                        const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src], q3 = os.slab[3][src];
+                        const float v2y = gel::sub(gel::i2f(py0 + lane), q0.y);
+                        const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
                         for(int xl = gx0 + ((warp - gx0) & (RASTER_WARPS - 1)); xl <= gx1; xl += RASTER_WARPS)
                         {
-                            float nv, nw;
-                            numerators(q0, q1, q2, gel::i2f(px0 + xl), fy, nv, nw);
+                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                            const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
+                            const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                            const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                            const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
                             if(nv < eps || nw < eps) continue;
                             const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
                             unsigned long long* k = sm.keys + xl * TH + lane;
                             if(key > *k) *k = key;
                         }
                     }
-                    __syncthreads();                                         /* slab / bbox / large_list reusable */
+                    __syncthreads();
                 }
                 if(!more) break;
             }

@@ -48,7 +48,7 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 4, stage_timing = 1;
-    float4* d_xf = nullptr; uint4 *d_entries = nullptr, *d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr;
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
     gelcu_view* d_views = nullptr; int views_cap = 0;
@@ -72,7 +72,7 @@ void free_work(gelcu_ctx* c)
 size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
 {
     const size_t frame = (size_t) c->xres * c->yres;
-    return 2 * frame * 8 + (size_t) c->nuniq * 16 + ((size_t) cap_e + cap_d) * 16 + (size_t) c->ntiles * NCHAIN * 4 + 64;
+    return 2 * frame * 8 + (size_t) c->nuniq * 16 + (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * NCHAIN * 4 + 64;
 }
 
 int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
@@ -81,7 +81,7 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
     free_work(c);
     const size_t frame = (size_t) c->xres * c->yres;
     CU(cudaMalloc(&c->d_xf, sizeof(float4) * std::max<size_t>(1, (size_t) B * c->nuniq)));
-    CU(cudaMalloc(&c->d_entries, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_e)));
+    CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) B * cap_e)));
     CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_d)));
     CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
     CU(cudaMalloc(&c->d_cursors, sizeof(int) * 2 * B));
@@ -459,10 +459,10 @@ int gelcu_debug_bins(gelcu_ctx* c, const gelcu_view* view, int* counts, int* ent
     if(rc < 0) return rc;
     const int ne = c->h_cursors[0], nd = c->h_cursors[1];
     std::vector<int> heads((size_t) c->ntiles * NCHAIN);
-    std::vector<uint4> desc(std::max(1, nd)), ent(std::max(1, ne));
+    std::vector<uint4> desc(std::max(1, nd)); std::vector<uint32_t> ent(std::max(1, ne));
     CU(cudaMemcpy(heads.data(), c->d_heads, sizeof(int) * heads.size(), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(desc.data(), c->d_descs, sizeof(uint4) * nd, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(ent.data(), c->d_entries, sizeof(uint4) * ne, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ent.data(), c->d_entries, sizeof(uint32_t) * ne, cudaMemcpyDeviceToHost));
     if(total) *total = ne;
     int w = 0;
     for(int t = 0; t < c->ntiles; t++)
@@ -470,7 +470,7 @@ int gelcu_debug_bins(gelcu_ctx* c, const gelcu_view* view, int* counts, int* ent
         std::vector<int> tris;
         for(int ch = 0; ch < NCHAIN; ch++)
             for(int cur = heads[(size_t) t * NCHAIN + ch]; cur >= 0; cur = (int) desc[cur].x)
-                for(uint32_t k = 0; k < desc[cur].z; k++) tris.push_back((int) ent[desc[cur].y + k].w);
+                for(uint32_t k = 0; k < desc[cur].z; k++) tris.push_back((int) ent[desc[cur].y + k]);
         std::sort(tris.begin(), tris.end());
         if(counts) counts[t] = (int) tris.size();
         for(size_t k = 0; k < tris.size() && entries && w < cap; k++) entries[w++] = tris[k];
