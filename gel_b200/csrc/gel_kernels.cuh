@@ -33,9 +33,9 @@ constexpr int TH = 32;             /* tile height (screen y, contiguous in memor
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int FRAG_MAX = 256;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
-constexpr int ROWS = 4;            /* rows per column unit                                                */
-constexpr int UNIT_WINDOW = 512;   /* column units staged per warp per pass                               */
-constexpr int QCAP = 160;          /* survivor stack per warp: < 32 left over + 32 lanes x ROWS           */
+constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
+constexpr int QCAP = 64;           /* survivor stack per warp: < 32 left over + one row of 32 lanes       */
+constexpr int MAX_BATCH = 256;     /* views per launch set (K3 keeps a per-view prefix in shared memory)  */
 constexpr int DEFER_MAX = 1024;    /* large triangles per round left to the CTA-wide sweep                */
 constexpr int SEG_SLOTS = 256;     /* segments staged per round (one per thread)                          */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
@@ -46,7 +46,7 @@ constexpr int LOCAL_MAX = 1024;    /* tile slots a K2 CTA can group locally     
 constexpr int HUGE_TILES = 16;     /* triangles covering more tiles than this are published tile by tile  */
 constexpr unsigned long long CLEAR_KEY = (0x00800000ull << 32) | 0xFFFFFFFFull;   /* zkey(-FLT_MAX), no winner */
 constexpr uint32_t FLAG_CLIPPED = 1u, FLAG_TEXCLAMP = 2u, FLAG_OVERFLOW = 0x80000000u;
-constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f;
+constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f, U_SLACK = 1.00001f;
 
 /* ------------------------------------------------------------------------------------------------ */
 /* K1: vertex transform                                                                             */
@@ -77,7 +77,9 @@ struct BinParams
     uint32_t* entries;   /* [view][cap_e]   triangle index                                                */
     uint4* descs;        /* [view][cap_d]   (next desc or -1, first entry, entry count, chunk)            */
     int* heads;          /* [view][ntiles][NCHAIN]  top of each chain, -1 = empty                         */
-    int* cursors;        /* [view][2]       entries used, descs used (keep counting past the capacity)    */
+    int* cursors;        /* [view][4]       entries used, descs used (both keep counting past the capacity), lit tiles, - */
+    int* tile_lit;       /* [view][ntiles]  1 once a segment was published for the tile                           */
+    int* lit_list;       /* [view][ntiles]  the lit tiles, in publication order                                   */
     uint32_t* flags;     /* [view]                                                                        */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d;
 };
@@ -87,6 +89,8 @@ __device__ __forceinline__ void publish_segment(const BinParams& p, int view, in
     int* head = p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + (chunk % NCHAIN);
     const int prev = atomicExch(head, id);
     p.descs[(size_t) view * p.cap_d + id] = make_uint4((uint32_t) prev, (uint32_t) first, (uint32_t) count, (uint32_t) chunk);
+    if(prev < 0 && atomicExch(p.tile_lit + (size_t) view * p.ntiles + tile, 1) == 0)
+        p.lit_list[(size_t) view * p.ntiles + atomicAdd(p.cursors + 4 * view + 2, 1)] = tile;
 }
 
 __global__ void __launch_bounds__(BIN_THREADS)
@@ -188,7 +192,7 @@ bin_kernel(BinParams p)
         if(tid == 0)
         {
             const int E = total & 0xFFFFF, S = total >> 20;
-            int* cur = p.cursors + 2 * view;
+            int* cur = p.cursors + 4 * view;
             const int eb = atomicAdd(cur, E), db = atomicAdd(cur + 1, S);
             s_ebase = eb; s_dbase = db;
             s_ok = (eb + E <= p.cap_e && db + S <= p.cap_d) ? 1 : 0;
@@ -235,7 +239,7 @@ bin_kernel(BinParams p)
         const int tx0 = rect[k] & 255, ty0 = (rect[k] >> 8) & 255, tx1 = (rect[k] >> 16) & 255, ty1 = (rect[k] >> 24) & 255;
         if(local && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= HUGE_TILES) continue;
         const uint32_t ent = (uint32_t) (chunk * BIN_CHUNK + k * BIN_THREADS + tid);
-        int* cur = p.cursors + 2 * view;
+        int* cur = p.cursors + 4 * view;
         for(int tx = tx0; tx <= tx1; tx++)
             for(int ty = ty0; ty <= ty1; ty++)
             {
@@ -251,13 +255,66 @@ bin_kernel(BinParams p)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* K3a: reset (main.c:413-417) of the tiles no triangle touches -- pure HBM stores, one warp per tile,  */
+/*      launched on a second stream so it overlaps the (instruction-bound) rasteriser                   */
+/* ------------------------------------------------------------------------------------------------ */
+
+template<bool HASH>
+__global__ void __launch_bounds__(256)
+clear_kernel(const int* __restrict__ tile_lit, uint32_t* __restrict__ pixel_base, float* __restrict__ z_base,
+             unsigned long long* __restrict__ hash, int ntiles, int tiles_y, int xres, int yres, int nviews)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(w >= ntiles * nviews) return;
+    const int view = w / ntiles, tile = w - view * ntiles;
+    if(__ldg(tile_lit + w)) return;
+    const int tx = tile / tiles_y, ty = tile - tx * tiles_y;
+    const int px0 = tx * TW, py0 = ty * TH;
+    const int px1 = min(px0 + TW, xres) - 1, py1 = min(py0 + TH, yres) - 1;
+    uint32_t* pixel = pixel_base + (size_t) view * xres * yres;
+    float* zbuf = z_base + (size_t) view * xres * yres;
+    if(!HASH && (yres & 3) == 0 && py1 - py0 + 1 == TH)
+    {
+        /* 8 lanes x 16 B = one 128-byte column of the tile; 4 columns per store instruction */
+        const int y = py0 + (lane & 7) * 4;
+        #pragma unroll
+        for(int k = 0; k < TW / 4; k++)
+        {
+            const int x = px0 + k * 4 + (lane >> 3);
+            if(x <= px1)
+            {
+                const size_t idx = (size_t) y + (size_t) x * yres;
+                *reinterpret_cast<uint4*>(pixel + idx) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<float4*>(zbuf + idx) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            }
+        }
+        return;
+    }
+    unsigned long long hp = 0, hz = 0;
+    const int y = py0 + lane;
+    if(y <= py1)
+        for(int x = px0; x <= px1; x++)
+        {
+            const int idx = y + x * yres;
+            pixel[idx] = 0u;
+            zbuf[idx] = -FLT_MAX;
+            if(HASH) { hp += gel::salt_mix(0u, (uint32_t) idx); hz += gel::salt_mix(0xFF7FFFFFu, (uint32_t) idx); }
+        }
+    if(HASH)
+    {
+        for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+        if(lane == 0) { atomicAdd(hash + 2 * view, hp); atomicAdd(hash + 2 * view + 1, hz); }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* K3: tile rasteriser                                                                              */
 /* ------------------------------------------------------------------------------------------------ */
 
 struct RasterParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
-    const uint32_t* entries; const uint4* descs; const int* heads;
+    const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list;
     const uint32_t* tex; int tw, th;
     uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
@@ -266,11 +323,12 @@ struct RasterParams
 /* per-warp scratch of the small-triangle path */
 struct WarpScratch
 {
-    float4 slab[4][32];                 /* 2 KB    per-triangle constants of the warp's current 32 entries          */
-    unsigned short unit[UNIT_WINDOW];   /* 1 KB    column unit -> (lane << 10 | x_local << 5 | first row)           */
-    float q_nv[QCAP], q_nw[QCAP];       /* 1.25 KB survivors of the sign test, waiting for the division stage       */
-    unsigned short q_id[QCAP];          /*         (lane << 10 | x_local << 5 | y_local)                            */
-    uint32_t bbox[32];                  /* clipped tile-local bbox: x0 | x1 << 5 | y0 << 10 | y1 << 15 | guard << 20 */
+    float4 slab[4][32];                 /* 2 KB   per-triangle constants of the warp's current 32 entries            */
+    unsigned short unit[UNIT_WINDOW];   /* 1 KB   column unit -> (lane << 5 | x_local)                               */
+    float2 q_n[QCAP];                   /* survivors of the cheap tests, waiting for the division stage: (nv, nw)     */
+    unsigned short q_id[QCAP];          /*                                                 lane << 10 | x << 5 | y    */
+    uint32_t bbox[32];                  /* clipped tile-local bbox: x0 | x1 << 5 | y0 << 10 | y1 << 15 | guard << 20  */
+    float den_hi[32];                   /* den * (1 + 1e-5): above it nv + nw means u < 0 for certain                 */
 };
 
 struct RasterSmem
@@ -280,10 +338,12 @@ struct RasterSmem
     int seg_first[SEG_SLOTS];
     int seg_pre[SEG_SLOTS];             /* exclusive prefix of the staged segment sizes */
     int defer[DEFER_MAX];               /* entry-pool indices of triangles left to the CTA-wide sweep */
+    int view_pre[MAX_BATCH + 1];        /* exclusive prefix of the views' lit-tile counts */
     int chain[NCHAIN];
     int warp_sums[RASTER_WARPS];
     unsigned long long hash[2];
-    int item, next_entry, ndefer;
+    int it_view, it_tile, it_tx, it_ty;
+    int next_entry, ndefer;
 };
 
 /* slab layout (den-sign normalised: if den < 0 the four Gram terms are negated, which negates both
@@ -313,6 +373,15 @@ __device__ __forceinline__ TriRecord make_record(const RasterParams& p, const fl
     return r;
 }
 
+/* Cheap tests that are EXACT rejections of main.c:352 (den > 0 after normalisation):
+ *   nv < -1e-20 (guard: den <= 1e18)  =>  v = nv/den is a negative non-zero float  =>  `v >= 0` fails; same for w
+ *   nv + nw > den*(1+1e-5)            =>  v + w > 1 + 9e-6 after rounding           =>  u = (1-v)-w < 0
+ * Everything else (including every NaN) goes on to the real divisions. */
+__device__ __forceinline__ bool may_be_inside(float nv, float nw, float eps, float den_hi)
+{
+    return !(nv < eps) && !(nw < eps) && !(gel::add(nv, nw) > den_hi);
+}
+
 /* division, inside test and depth of main.c:327-329, 352, 355; returns the key, or 0 when outside */
 __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, float den, const float4& q3)
 {
@@ -327,9 +396,10 @@ __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, f
 __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws, int i)
 {
     const uint32_t id = ws.q_id[i];
-    const int src = id >> 10, xl = (id >> 5) & 31, yl = id & 31;
-    const unsigned long long key = fragment_key(ws.q_nv[i], ws.q_nw[i], ws.slab[2][src].w, ws.slab[3][src]);
-    unsigned long long* k = sm.keys + xl * TH + yl;
+    const float2 n = ws.q_n[i];
+    const int src = id >> 10;
+    const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
+    unsigned long long* k = sm.keys + (id & 1023);           /* x_local*TH + y_local */
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
 
@@ -342,17 +412,53 @@ raster_kernel(RasterParams p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpScratch& ws = sm.ws[warp];
-    const int nitems = p.nviews * p.ntiles;
-    const bool vec_ok = (p.yres & 3) == 0;
+
+    /* work list = the lit tiles of every view, view-major: prefix of the per-view counts K2 left in cursors[view][2] */
+    {
+        const int c = tid < p.nviews ? __ldg(p.cursors + 4 * tid + 2) : 0;
+        int incl = c;
+        for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+        if(lane == 31) sm.warp_sums[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for(int w = 0; w < warp; w++) wbase += sm.warp_sums[w];
+        sm.view_pre[tid] = wbase + incl - c;
+        if(tid == RASTER_THREADS - 1) sm.view_pre[MAX_BATCH] = wbase + incl;
+        __syncthreads();
+    }
+    const int nitems = sm.view_pre[MAX_BATCH];
+
+    /* thread 0 owns the work queue: the atomic for the NEXT item is issued when the current tile starts and its
+     * result is only consumed after the tile's visibility pass, so the round trip hides behind real work */
+    int nx_view = -1, nx_tile = 0, g_next = 0;
+    auto locate = [&](int g) {
+        nx_view = -1;
+        if(g < nitems)
+        {
+            int lo = 0;
+            #pragma unroll
+            for(int step = MAX_BATCH / 2; step; step >>= 1) if(lo + step < p.nviews && sm.view_pre[lo + step] <= g) lo += step;
+            nx_view = lo;
+            nx_tile = __ldg(p.lit_list + (size_t) lo * p.ntiles + (g - sm.view_pre[lo]));
+        }
+    };
+    if(tid == 0) locate(atomicAdd(p.work_counter, 1));
+
     for(;;)
     {
-        if(tid == 0) { sm.item = atomicAdd(p.work_counter, 1); sm.hash[0] = 0; sm.hash[1] = 0; }
+        if(tid == 0)
+        {
+            sm.it_view = nx_view; sm.it_tile = nx_tile;
+            const int tx = nx_tile / p.tiles_y;
+            sm.it_tx = tx; sm.it_ty = nx_tile - tx * p.tiles_y;
+            sm.hash[0] = 0; sm.hash[1] = 0;
+        }
         __syncthreads();
-        const int item = sm.item;
-        if(item >= nitems) break;
-        const int view = item / p.ntiles, tile = item - view * p.ntiles;
-        const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
-        const int px0 = tx * TW, py0 = ty * TH;
+        const int view = sm.it_view;
+        if(view < 0) break;
+        if(tid == 0) g_next = atomicAdd(p.work_counter, 1);
+        const int tile = sm.it_tile;
+        const int px0 = sm.it_tx * TW, py0 = sm.it_ty * TH;
         const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
         uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
         float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
@@ -361,243 +467,221 @@ raster_kernel(RasterParams p)
         const uint32_t* entries = p.entries + (size_t) view * p.cap_e;
         unsigned long long hp = 0, hz = 0;
 
-        int head = -1;
-        if(tid < NCHAIN) { head = __ldg(p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + tid); sm.chain[tid] = head; }
-        const bool empty = __syncthreads_and(head < 0);
+        if(tid < NCHAIN) sm.chain[tid] = __ldg(p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + tid);
+        for(int i = tid; i < TW * TH; i += RASTER_THREADS) sm.keys[i] = CLEAR_KEY;
 
-        if(empty)
+        /* ================= visibility: every (triangle, pixel) of main.c:348-356 inside this tile ================= */
+        for(;;)
         {
-            /* reset (main.c:413-417) for a tile nothing touches: straight to HBM */
-            if(!HASH && vec_ok && py1 - py0 + 1 == TH)
+            /* ---- stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) ---- */
+            if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
+            __syncthreads();
+            if(tid < NCHAIN)
             {
-                const int x = px0 + (tid >> 3), y = py0 + (tid & 7) * 4;
-                if(x <= px1)
+                int cur = sm.chain[tid], k = 0;
+                while(cur >= 0 && k < SEG_SLOTS / NCHAIN)
                 {
-                    const size_t idx = (size_t) y + (size_t) x * p.yres;
-                    *reinterpret_cast<uint4*>(pixel + idx) = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<float4*>(zbuf + idx) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                    const uint4 d = __ldg(descs + cur);
+                    sm.seg_first[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.y;
+                    sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.z;      /* size for now */
+                    cur = (int) d.x; k++;
                 }
+                for(; k < SEG_SLOTS / NCHAIN; k++) sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = 0;
+                sm.chain[tid] = cur;
             }
-            else
-                for(int i = tid; i < TW * TH; i += RASTER_THREADS)
-                {
-                    const int x = px0 + (i >> 5), y = py0 + (i & 31);
-                    if(x <= px1 && y <= py1)
-                    {
-                        const int idx = y + x * p.yres;
-                        pixel[idx] = 0u;
-                        zbuf[idx] = -FLT_MAX;
-                        if(HASH) { hp += gel::salt_mix(0u, (uint32_t) idx); hz += gel::salt_mix(0xFF7FFFFFu, (uint32_t) idx); }
-                    }
-                }
-        }
-        else
-        {
-            for(int i = tid; i < TW * TH; i += RASTER_THREADS) sm.keys[i] = CLEAR_KEY;
+            const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
+            const int my_count = sm.seg_pre[tid];
+            int incl = my_count;
+            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+            if(lane == 31) sm.warp_sums[warp] = incl;
+            __syncthreads();
+            int wbase = 0, round_entries = 0;
+            #pragma unroll
+            for(int w = 0; w < RASTER_WARPS; w++) { const int x = sm.warp_sums[w]; if(w < warp) wbase += x; round_entries += x; }
+            sm.seg_pre[tid] = wbase + incl - my_count;
+            __syncthreads();
 
-            /* ================= visibility: every (triangle, pixel) of main.c:348-356 inside this tile ================= */
+            /* ---- small triangles: every warp pulls 32 entries at a time, no CTA barrier inside ---- */
+            int qn = 0;                                                   /* survivors on the warp's stack (warp-uniform) */
             for(;;)
             {
-                /* ---- stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) ---- */
-                if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
-                __syncthreads();
-                if(tid < NCHAIN)
+                int e0 = 0;
+                if(lane == 0) e0 = atomicAdd(&sm.next_entry, 32);
+                e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+                if(e0 >= round_entries) break;
+                const int e = e0 + lane;
+                int nun = 0, x = 0;
+                if(e < round_entries)
                 {
-                    int cur = sm.chain[tid], k = 0;
-                    while(cur >= 0 && k < SEG_SLOTS / NCHAIN)
+                    /* staged segment holding entry e: last slot with seg_pre <= e */
+                    int lo = 0;
+                    #pragma unroll
+                    for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
+                    const int pool = sm.seg_first[lo] + (e - sm.seg_pre[lo]);
+                    const TriRecord r = make_record(p, xf, __ldg(entries + pool), px0, py0, px1, py1);
+                    bool unitised = r.npx > 0;
+                    if(r.npx > FRAG_MAX)
                     {
-                        const uint4 d = __ldg(descs + cur);
-                        sm.seg_first[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.y;
-                        sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.z;      /* size for now */
-                        cur = (int) d.x; k++;
+                        const int slot = atomicAdd(&sm.ndefer, 1);
+                        if(slot < DEFER_MAX) { sm.defer[slot] = pool; unitised = false; }
                     }
-                    for(; k < SEG_SLOTS / NCHAIN; k++) sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = 0;
-                    sm.chain[tid] = cur;
-                }
-                const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
-                const int my_count = sm.seg_pre[tid];
-                int incl = my_count;
-                for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
-                if(lane == 31) sm.warp_sums[warp] = incl;
-                __syncthreads();
-                int wbase = 0, round_entries = 0;
-                #pragma unroll
-                for(int w = 0; w < RASTER_WARPS; w++) { const int x = sm.warp_sums[w]; if(w < warp) wbase += x; round_entries += x; }
-                sm.seg_pre[tid] = wbase + incl - my_count;
-                __syncthreads();
-
-                /* ---- small triangles: every warp pulls 32 entries at a time, no CTA barrier inside ---- */
-                int qn = 0;                                                   /* survivors on the warp's stack (warp-uniform) */
-                for(;;)
-                {
-                    int e0 = 0;
-                    if(lane == 0) e0 = atomicAdd(&sm.next_entry, 32);
-                    e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
-                    if(e0 >= round_entries) break;
-                    const int e = e0 + lane;
-                    int nun = 0, bx0 = 0, by0 = 0, by1 = -1;
-                    if(e < round_entries)
+                    if(unitised)
                     {
-                        /* staged segment holding entry e: last slot with seg_pre <= e */
-                        int lo = 0;
-                        #pragma unroll
-                        for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
-                        const int pool = sm.seg_first[lo] + (e - sm.seg_pre[lo]);
-                        const TriRecord r = make_record(p, xf, __ldg(entries + pool), px0, py0, px1, py1);
-                        bool unitised = r.npx > 0;
-                        if(r.npx > FRAG_MAX)
-                        {
-                            const int slot = atomicAdd(&sm.ndefer, 1);
-                            if(slot < DEFER_MAX) { sm.defer[slot] = pool; unitised = false; }
-                        }
-                        if(unitised)
-                        {
-                            bx0 = r.bbox & 31; by0 = (r.bbox >> 10) & 31; by1 = (r.bbox >> 15) & 31;
-                            const int bx1 = (r.bbox >> 5) & 31;
-                            nun = (bx1 - bx0 + 1) * ((by1 - by0 + ROWS) / ROWS);
-                            ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
-                            ws.bbox[lane] = r.bbox;
-                        }
-                    }
-                    int uincl = nun;
-                    for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
-                    const int ustart = uincl - nun;
-                    const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
-                    int emitted = 0, x = bx0, yb = by0;
-                    __syncwarp();
-                    for(int w0 = 0; w0 < utotal; w0 += UNIT_WINDOW)
-                    {
-                        /* expansion: one 16-bit word per column unit (a column of the bbox, at most ROWS rows) */
-                        while(emitted < nun && ustart + emitted < w0 + UNIT_WINDOW)
-                        {
-                            ws.unit[ustart + emitted - w0] = (unsigned short) (lane << 10 | x << 5 | yb);
-                            emitted++;
-                            yb += ROWS;
-                            if(yb > by1) { yb = by0; x++; }
-                        }
-                        __syncwarp();
-                        const int n = min(UNIT_WINDOW, utotal - w0);
-                        for(int u0 = 0; u0 < n; u0 += 32)
-                        {
-                            /* stage 1: numerators of v and w (main.c:325-328) for the unit's rows; exact sign early-out */
-                            const bool act = u0 + lane < n;
-                            const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
-                            const int src = o >> 10, xl = (o >> 5) & 31, y0l = o & 31;
-                            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
-                            const uint32_t bb = ws.bbox[src];
-                            const int rows = act ? min(ROWS, (int) ((bb >> 15) & 31) - y0l + 1) : 0;
-                            const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
-                            const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
-                            #pragma unroll
-                            for(int r = 0; r < ROWS; r++)
-                            {
-                                const float v2y = gel::sub(gel::i2f(py0 + y0l + r), q0.y);
-                                const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
-                                const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
-                                const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
-                                const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                                /* nv < eps: the quotient nv/den is a negative NON-ZERO float, so main.c:352 fails */
-                                const bool pass = r < rows && !(nv < eps) && !(nw < eps);
-                                const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-                                if(pass)
-                                {
-                                    const int slot = qn + __popc(m & lt_mask);
-                                    ws.q_id[slot] = (unsigned short) (src << 10 | xl << 5 | (y0l + r));
-                                    ws.q_nv[slot] = nv; ws.q_nw[slot] = nw;
-                                }
-                                qn += __popc(m);
-                            }
-                            __syncwarp();
-                            /* stage 2: divisions, inside test, depth, key -- full warps off the top of the stack */
-                            while(qn >= 32) { qn -= 32; resolve_survivor(sm, ws, qn + lane); }
-                            __syncwarp();
-                        }
-                    }
-                    if(lane < qn) resolve_survivor(sm, ws, lane);
-                    qn = 0;
-                    __syncwarp();
-                }
-                __syncthreads();
-
-                /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
-                 *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
-                const int ndefer = min(sm.ndefer, DEFER_MAX);
-                for(int base = 0; base < ndefer; base += RASTER_THREADS)
-                {
-                    if(base + tid < ndefer)
-                    {
-                        const TriRecord r = make_record(p, xf, __ldg(entries + sm.defer[base + tid]), px0, py0, px1, py1);
+                        x = r.bbox & 31;
+                        nun = (int) ((r.bbox >> 5) & 31) - x + 1;             /* one unit per bbox column */
                         ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
                         ws.bbox[lane] = r.bbox;
+                        ws.den_hi[lane] = r.q2.w * U_SLACK;
                     }
-                    __syncthreads();
-                    const int cnt = min(RASTER_THREADS, ndefer - base);
-                    for(int li = 0; li < cnt; li++)
+                }
+                int uincl = nun;
+                for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
+                const int ustart = uincl - nun;
+                const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
+                int emitted = 0;
+                __syncwarp();
+                for(int w0 = 0; w0 < utotal; w0 += UNIT_WINDOW)
+                {
+                    /* expansion: one 16-bit word per column unit */
+                    while(emitted < nun && ustart + emitted < w0 + UNIT_WINDOW)
                     {
-                        const WarpScratch& os = sm.ws[li >> 5];
-                        const int src = li & 31;
-                        const uint32_t bb = os.bbox[src];
-                        const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
-                        if(lane < gy0 || lane > gy1) continue;
+                        ws.unit[ustart + emitted - w0] = (unsigned short) (lane << 5 | (x + emitted));
+                        emitted++;
+                    }
+                    __syncwarp();
+                    const int n = min(UNIT_WINDOW, utotal - w0);
+                    for(int u0 = 0; u0 < n; u0 += 32)
+                    {
+                        /* stage 1: numerators of v and w (main.c:325-328) down the column; exact cheap rejections */
+                        const bool act = u0 + lane < n;
+                        const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
+                        const int src = o >> 5, xl = o & 31;
+                        const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
+                        const uint32_t bb = ws.bbox[src];
+                        const float den_hi = ws.den_hi[src];
+                        const int y0l = (bb >> 10) & 31;
+                        const int rows = act ? (int) ((bb >> 15) & 31) - y0l + 1 : 0;
+                        const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
                         const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                        const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src], q3 = os.slab[3][src];
-                        const float v2y = gel::sub(gel::i2f(py0 + lane), q0.y);
-                        const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
-                        for(int xl = gx0 + ((warp - gx0) & (RASTER_WARPS - 1)); xl <= gx1; xl += RASTER_WARPS)
+                        const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                        const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
+                        float fy = gel::i2f(py0 + y0l);
+                        uint32_t id = (uint32_t) src << 10 | (uint32_t) xl << 5 | (uint32_t) y0l;
+                        for(int r = 0; r < maxrows; r++, id++)
                         {
-                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
-                            const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
-                            const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                            const float v2y = gel::sub(fy, q0.y);
+                            fy = gel::add(fy, 1.0f);                          /* exact: small integers */
+                            const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
+                            const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
                             const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
                             const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                            if(nv < eps || nw < eps) continue;
-                            const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
-                            unsigned long long* k = sm.keys + xl * TH + lane;
-                            if(key > *k) *k = key;
+                            const bool pass = r < rows && may_be_inside(nv, nw, eps, den_hi);
+                            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                            if(pass)
+                            {
+                                const int slot = qn + __popc(m & lt_mask);
+                                ws.q_id[slot] = (unsigned short) id;
+                                ws.q_n[slot] = make_float2(nv, nw);
+                            }
+                            qn += __popc(m);
+                            if(qn >= 32)
+                            {
+                                /* stage 2: divisions, inside test, depth, key -- a full warp off the top of the stack */
+                                __syncwarp();
+                                qn -= 32;
+                                resolve_survivor(sm, ws, qn + lane);
+                                __syncwarp();
+                            }
                         }
                     }
-                    __syncthreads();
+                    __syncwarp();
                 }
-                if(!more) break;
+                __syncwarp();
+                if(lane < qn) resolve_survivor(sm, ws, lane);
+                qn = 0;
+                __syncwarp();
             }
             __syncthreads();
 
-            /* ================= shade the winner of every pixel once (main.c:358-366), write the tile back ================= */
-            for(int i = tid; i < TW * TH; i += RASTER_THREADS)
+            /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
+             *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
+            const int ndefer = min(sm.ndefer, DEFER_MAX);
+            for(int base = 0; base < ndefer; base += RASTER_THREADS)
             {
-                const int x = px0 + (i >> 5), y = py0 + (i & 31);
-                if(x > px1 || y > py1) continue;
-                const unsigned long long key = sm.keys[i];
-                uint32_t colour = 0u;
-                float z = -FLT_MAX;
-                if(key != CLEAR_KEY)
+                if(base + tid < ndefer)
                 {
-                    const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
-                    z = gel::zkey_inv((uint32_t) (key >> 32));
-                    const float4 a = __ldg(xf + __ldg(p.i0 + tri));
-                    const float4 b = __ldg(xf + __ldg(p.i1 + tri));
-                    const float4 c = __ldg(xf + __ldg(p.i2 + tri));
-                    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
-                    float nv, nw, v, w, u, zz;
-                    gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
-                    gel::bary_inside(s, nv, nw, v, w, u, zz);
-                    const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
-                    const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
-                    int xx, yy, shading;
-                    gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
-                    if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
-                    {
-                        atomicOr(p.flags + view, FLAG_TEXCLAMP);   /* the reference reads out of bounds here (R) */
-                        xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
-                    }
-                    colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+                    const TriRecord r = make_record(p, xf, __ldg(entries + sm.defer[base + tid]), px0, py0, px1, py1);
+                    ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
+                    ws.bbox[lane] = r.bbox;
                 }
-                const int idx = y + x * p.yres;
-                pixel[idx] = colour;
-                zbuf[idx] = z;
-                if(HASH) { hp += gel::salt_mix(colour, (uint32_t) idx); hz += gel::salt_mix(__float_as_uint(z), (uint32_t) idx); }
+                __syncthreads();
+                const int cnt = min(RASTER_THREADS, ndefer - base);
+                for(int li = 0; li < cnt; li++)
+                {
+                    const WarpScratch& os = sm.ws[li >> 5];
+                    const int src = li & 31;
+                    const uint32_t bb = os.bbox[src];
+                    const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
+                    if(lane < gy0 || lane > gy1) continue;
+                    const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
+                    const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src], q3 = os.slab[3][src];
+                    const float den_hi = q2.w * U_SLACK;
+                    const float v2y = gel::sub(gel::i2f(py0 + lane), q0.y);
+                    const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
+                    for(int xl = gx0 + ((warp - gx0) & (RASTER_WARPS - 1)); xl <= gx1; xl += RASTER_WARPS)
+                    {
+                        const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                        const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
+                        const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                        const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                        const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                        if(!may_be_inside(nv, nw, eps, den_hi)) continue;
+                        const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
+                        unsigned long long* k = sm.keys + xl * TH + lane;
+                        if(key > *k) *k = key;
+                    }
+                }
+                __syncthreads();
             }
+            if(!more) break;
+        }
+        __syncthreads();
+        if(tid == 0) locate(g_next);
+
+        /* ================= shade the winner of every pixel once (main.c:358-366), write the tile back ================= */
+        for(int i = tid; i < TW * TH; i += RASTER_THREADS)
+        {
+            const int x = px0 + (i >> 5), y = py0 + (i & 31);
+            if(x > px1 || y > py1) continue;
+            const unsigned long long key = sm.keys[i];
+            uint32_t colour = 0u;
+            float z = -FLT_MAX;
+            if(key != CLEAR_KEY)
+            {
+                const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
+                z = gel::zkey_inv((uint32_t) (key >> 32));
+                const float4 a = __ldg(xf + __ldg(p.i0 + tri));
+                const float4 b = __ldg(xf + __ldg(p.i1 + tri));
+                const float4 c = __ldg(xf + __ldg(p.i2 + tri));
+                const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+                float nv, nw, v, w, u, zz;
+                gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+                gel::bary_inside(s, nv, nw, v, w, u, zz);
+                const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
+                const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
+                int xx, yy, shading;
+                gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
+                if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
+                {
+                    atomicOr(p.flags + view, FLAG_TEXCLAMP);   /* the reference reads out of bounds here (R) */
+                    xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
+                }
+                colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+            }
+            const int idx = y + x * p.yres;
+            pixel[idx] = colour;
+            zbuf[idx] = z;
+            if(HASH) { hp += gel::salt_mix(colour, (uint32_t) idx); hz += gel::salt_mix(__float_as_uint(z), (uint32_t) idx); }
         }
         if(HASH)
         {

@@ -40,7 +40,8 @@ template<typename T> void dfree(T*& p) { if(p) cudaFree(p); p = nullptr; }
 struct gelcu_ctx
 {
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, clear_stream = nullptr;
+    cudaEvent_t bin_done = nullptr, clear_done = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr;
@@ -48,7 +49,7 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 4, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr;
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
     gelcu_view* d_views = nullptr; int views_cap = 0;
@@ -63,7 +64,7 @@ namespace {
 
 void free_work(gelcu_ctx* c)
 {
-    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors);
+    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]);
     c->batch = 0; c->cap_e = 0; c->cap_d = 0;
@@ -72,7 +73,7 @@ void free_work(gelcu_ctx* c)
 size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
 {
     const size_t frame = (size_t) c->xres * c->yres;
-    return 2 * frame * 8 + (size_t) c->nuniq * 16 + (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * NCHAIN * 4 + 64;
+    return 2 * frame * 8 + (size_t) c->nuniq * 16 + (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * (NCHAIN + 2) * 4 + 64;
 }
 
 int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
@@ -84,7 +85,9 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
     CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) B * cap_e)));
     CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_d)));
     CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
-    CU(cudaMalloc(&c->d_cursors, sizeof(int) * 2 * B));
+    CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
+    CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
+    CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
     CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
     CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
     CU(cudaMalloc(&c->d_work, sizeof(int)));
@@ -99,9 +102,9 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
 
 int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 {
-    if(c->batch_opt > 0) return c->batch_opt;
+    if(c->batch_opt > 0) return std::min(c->batch_opt, MAX_BATCH);
     const size_t budget = (size_t) 24 << 30;
-    return (int) std::min<size_t>(256, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));
+    return (int) std::min<size_t>(MAX_BATCH, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));
 }
 
 /* Enqueues K1..K3 for `n` views starting at d_views + first into frame buffer `buf`. */
@@ -109,7 +112,8 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
 {
     cudaStream_t s = c->stream;
     CU(cudaMemsetAsync(c->d_heads, 0xFF, sizeof(int) * (size_t) n * c->ntiles * NCHAIN, s));
-    CU(cudaMemsetAsync(c->d_cursors, 0, sizeof(int) * 2 * n, s));
+    CU(cudaMemsetAsync(c->d_cursors, 0, sizeof(int) * 4 * n, s));
+    CU(cudaMemsetAsync(c->d_tile_lit, 0, sizeof(int) * (size_t) n * c->ntiles, s));
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t) * n, s));
     CU(cudaMemsetAsync(c->d_work, 0, sizeof(int), s));
     if(want_hash) CU(cudaMemsetAsync(c->d_hash, 0, sizeof(unsigned long long) * 2 * n, s));
@@ -122,20 +126,33 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
     CU(cudaEventRecord(ev4[1], s));
     if(c->ntri > 0)
     {
-        BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_flags,
+        BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
                          c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d };
         bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
         c->stats.kernels_launched++;
     }
     CU(cudaEventRecord(ev4[2], s));
-    RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads,
+    /* K3a on its own stream: untouched tiles are plain HBM stores and overlap the instruction-bound rasteriser */
+    CU(cudaEventRecord(c->bin_done, s));
+    CU(cudaStreamWaitEvent(c->clear_stream, c->bin_done, 0));
+    {
+        const int warps = n * c->ntiles, blocks = (warps + 7) / 8;
+        if(want_hash) clear_kernel<true><<<blocks, 256, 0, c->clear_stream>>>(c->d_tile_lit, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->ntiles, c->tiles_y, c->xres, c->yres, n);
+        else clear_kernel<false><<<blocks, 256, 0, c->clear_stream>>>(c->d_tile_lit, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->ntiles, c->tiles_y, c->xres, c->yres, n);
+        c->stats.kernels_launched++;
+    }
+    CU(cudaEventRecord(c->clear_done, c->clear_stream));
+    RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list,
                         c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
                         c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
-    const int items = n * c->ntiles;
-    const int grid = std::max(1, std::min(items, c->num_sms * c->ctas_per_sm));
-    if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-    else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-    c->stats.kernels_launched++;
+    const int grid = c->num_sms * c->ctas_per_sm;
+    if(c->ntri > 0)
+    {
+        if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        c->stats.kernels_launched++;
+    }
+    CU(cudaStreamWaitEvent(s, c->clear_done, 0));
     CU(cudaEventRecord(ev4[3], s));
     CU(cudaGetLastError());
     return GELCU_OK;
@@ -156,7 +173,7 @@ int ensure_host(gelcu_ctx* c, int n)
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
     c->h_cursors = nullptr; c->h_flags = nullptr; c->hcap = 0;
-    CU(cudaMallocHost(&c->h_cursors, sizeof(int) * 2 * n));
+    CU(cudaMallocHost(&c->h_cursors, sizeof(int) * 4 * n));
     CU(cudaMallocHost(&c->h_flags, sizeof(uint32_t) * n));
     c->hcap = n;
     return GELCU_OK;
@@ -206,6 +223,9 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     cudaError_t s1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t s2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->clear_stream, cudaStreamNonBlocking);
+    if(s1 == cudaSuccess) s1 = cudaEventCreateWithFlags(&c->bin_done, cudaEventDisableTiming);
+    if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->clear_done, cudaEventDisableTiming);
     for(int k = 0; k < 2 && s1 == cudaSuccess && s2 == cudaSuccess; k++)
     {
         s1 = cudaEventCreateWithFlags(&c->render_done[k], cudaEventDisableTiming);
@@ -365,7 +385,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
             rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, &c->ev[4 * b]); if(rc) return rc;
             /* small per-batch results ride the render stream (the next batch overwrites their device copies) */
-            CU(cudaMemcpyAsync(c->h_cursors + 2 * first, c->d_cursors, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(c->h_cursors + 4 * first, c->d_cursors, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaMemcpyAsync(c->h_flags + first, c->d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
             if(hash_out) { CU(cudaMemcpyAsync(hash_out + 2 * (size_t) first, c->d_hash, 16 * (size_t) n, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2h_bytes += 16 * (size_t) n; }
             CU(cudaEventRecord(c->render_done[buf], c->stream));
@@ -375,13 +395,14 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         if(pixel_out || z_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(c->clear_stream));
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
         for(int v = 0; v < nviews; v++)
         {
             flags |= c->h_flags[v];
-            need_e = std::max(need_e, c->h_cursors[2 * v]); need_d = std::max(need_d, c->h_cursors[2 * v + 1]);
-            entries += (uint64_t) c->h_cursors[2 * v];
+            need_e = std::max(need_e, c->h_cursors[4 * v]); need_d = std::max(need_d, c->h_cursors[4 * v + 1]);
+            entries += (uint64_t) c->h_cursors[4 * v];
         }
         if(flags & FLAG_OVERFLOW)
         {
@@ -501,6 +522,9 @@ void gelcu_destroy(gelcu_ctx* c)
     for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); }
     if(c->stream) cudaStreamDestroy(c->stream);
     if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if(c->clear_stream) cudaStreamDestroy(c->clear_stream);
+    if(c->bin_done) cudaEventDestroy(c->bin_done);
+    if(c->clear_done) cudaEventDestroy(c->clear_done);
     delete c;
 }
 
