@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="library batch_views option (0 = default)")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg2/cfg5 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="library tunable name=value (gelcu_set_option), repeatable")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = dist_env()
@@ -353,6 +354,8 @@ def main():
     r.set_texture(inputs["tex"])
     if args.batch:
         r.set_option("batch_views", args.batch)
+    for o in args.opt:
+        r.set_option(o.split("=")[0], int(o.split("=")[1]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     # lit pixels L of this rank's first view (for B_alg), read back once outside any timed region

@@ -63,7 +63,7 @@ def cu() -> ctypes.CDLL:
     """libgelcu.so with argtypes set."""
     global _cu
     if _cu is None:
-        L = _load("libgelcu.so")
+        L = _load(os.environ.get("GELCU_LIB", "libgelcu.so"))   # GELCU_LIB: tuning variants built by scripts/
         L.gelcu_device_count.restype = c_int
         L.gelcu_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int]
         L.gelcu_set_mesh.argtypes = [c_void_p, _fp, _fp, _fp, c_int]

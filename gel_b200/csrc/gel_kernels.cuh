@@ -30,14 +30,24 @@ namespace gelk {
 
 constexpr int TW = 32;             /* tile width  (screen x, the framebuffer's SLOW axis)                */
 constexpr int TH = 32;             /* tile height (screen y, contiguous in memory: index y + x*yres)     */
-constexpr int RASTER_THREADS = 256;
+#ifndef GEL_RASTER_THREADS
+#define GEL_RASTER_THREADS 128
+#endif
+#ifndef GEL_GRAB
+#define GEL_GRAB 32
+#endif
+constexpr int RASTER_THREADS = GEL_RASTER_THREADS;
+constexpr int GRAB = GEL_GRAB;        /* entries a warp pulls from the tile's list per queue access (32 or 64) */
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int FRAG_MAX = 256;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
 constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
 constexpr int QCAP = 64;           /* survivor stack per warp: < 32 left over + one row of 32 lanes       */
+constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16 B each, global scratch)   */
+constexpr int TWO_PHASE_MIN = 128;  /* tiles with fewer entries are rasterised in one phase                */
 constexpr int MAX_BATCH = 256;     /* views per launch set (K3 keeps a per-view prefix in shared memory)  */
-constexpr int DEFER_MAX = 1024;    /* large triangles per round left to the CTA-wide sweep                */
-constexpr int SEG_SLOTS = 256;     /* segments staged per round (one per thread)                          */
+constexpr int DEFER_MAX = 256;     /* large triangles per round left to the CTA-wide sweep                */
+constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
+constexpr int SEG_SLOTS = RASTER_THREADS;   /* segments staged per round (one per thread)                 */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_TPT = 4;         /* triangles per thread in K2                                          */
@@ -54,17 +64,29 @@ constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f, U_SLACK = 1.00001f;
 
 __global__ void __launch_bounds__(256)
 transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict__ vpos,
-                 const float4* __restrict__ vnrm, float4* __restrict__ xf, int nuniq, int xres, int yres)
+                 const float4* __restrict__ vnrm, float4* __restrict__ xf, uint32_t* __restrict__ zrange, int nuniq, int xres, int yres)
 {
+    __shared__ uint32_t s_lo, s_hi;
     const int view = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= nuniq) return;
-    const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
-    const float4 p = __ldg(vpos + i);
-    const float4 n = __ldg(vnrm + i);
-    float4 o;
-    gel::transform_corner(c, p.x, p.y, p.z, n.x, n.y, n.z, o.x, o.y, o.z, o.w);
-    xf[(size_t) view * nuniq + i] = o;
+    if(threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+    __syncthreads();
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    if(i < nuniq)
+    {
+        const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
+        const float4 p = __ldg(vpos + i);
+        const float4 n = __ldg(vnrm + i);
+        float4 o;
+        gel::transform_corner(c, p.x, p.y, p.z, n.x, n.y, n.z, o.x, o.y, o.z, o.w);
+        xf[(size_t) view * nuniq + i] = o;
+        if(o.z == o.z) lo = hi = gel::zkey(o.z);
+    }
+    /* range of the view's screen depths: the rasteriser splits near / far triangles at its midpoint */
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if((threadIdx.x & 31) == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    if(threadIdx.x == 0) { atomicMin(zrange + 2 * view, s_lo); atomicMax(zrange + 2 * view + 1, s_hi); }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -255,68 +277,16 @@ bin_kernel(BinParams p)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* K3a: reset (main.c:413-417) of the tiles no triangle touches -- pure HBM stores, one warp per tile,  */
-/*      launched on a second stream so it overlaps the (instruction-bound) rasteriser                   */
-/* ------------------------------------------------------------------------------------------------ */
-
-template<bool HASH>
-__global__ void __launch_bounds__(256)
-clear_kernel(const int* __restrict__ tile_lit, uint32_t* __restrict__ pixel_base, float* __restrict__ z_base,
-             unsigned long long* __restrict__ hash, int ntiles, int tiles_y, int xres, int yres, int nviews)
-{
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if(w >= ntiles * nviews) return;
-    const int view = w / ntiles, tile = w - view * ntiles;
-    if(__ldg(tile_lit + w)) return;
-    const int tx = tile / tiles_y, ty = tile - tx * tiles_y;
-    const int px0 = tx * TW, py0 = ty * TH;
-    const int px1 = min(px0 + TW, xres) - 1, py1 = min(py0 + TH, yres) - 1;
-    uint32_t* pixel = pixel_base + (size_t) view * xres * yres;
-    float* zbuf = z_base + (size_t) view * xres * yres;
-    if(!HASH && (yres & 3) == 0 && py1 - py0 + 1 == TH)
-    {
-        /* 8 lanes x 16 B = one 128-byte column of the tile; 4 columns per store instruction */
-        const int y = py0 + (lane & 7) * 4;
-        #pragma unroll
-        for(int k = 0; k < TW / 4; k++)
-        {
-            const int x = px0 + k * 4 + (lane >> 3);
-            if(x <= px1)
-            {
-                const size_t idx = (size_t) y + (size_t) x * yres;
-                *reinterpret_cast<uint4*>(pixel + idx) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<float4*>(zbuf + idx) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-            }
-        }
-        return;
-    }
-    unsigned long long hp = 0, hz = 0;
-    const int y = py0 + lane;
-    if(y <= py1)
-        for(int x = px0; x <= px1; x++)
-        {
-            const int idx = y + x * yres;
-            pixel[idx] = 0u;
-            zbuf[idx] = -FLT_MAX;
-            if(HASH) { hp += gel::salt_mix(0u, (uint32_t) idx); hz += gel::salt_mix(0xFF7FFFFFu, (uint32_t) idx); }
-        }
-    if(HASH)
-    {
-        for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
-        if(lane == 0) { atomicAdd(hash + 2 * view, hp); atomicAdd(hash + 2 * view + 1, hz); }
-    }
-}
-
-/* ------------------------------------------------------------------------------------------------ */
 /* K3: tile rasteriser                                                                              */
 /* ------------------------------------------------------------------------------------------------ */
 
 struct RasterParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
-    const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list;
+    const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list; const int* tile_lit;
+    const uint32_t* zrange; uint4* far_scratch;
     const uint32_t* tex; int tw, th;
-    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;
+    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;   /* [0] lit-tile queue, [1] reset queue */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
 };
 
@@ -342,8 +312,10 @@ struct RasterSmem
     int chain[NCHAIN];
     int warp_sums[RASTER_WARPS];
     unsigned long long hash[2];
-    int it_view, it_tile, it_tx, it_ty;
-    int next_entry, ndefer;
+    uint32_t hiz[16];                   /* per 8x8 block: min over its pixels of the depth key (after the near phase) */
+    int it_view, it_tile, it_tx, it_ty, it_clear;
+    int next_entry, ndefer, nfar;
+    float zthr;
 };
 
 /* slab layout (den-sign normalised: if den < 0 the four Gram terms are negated, which negates both
@@ -353,9 +325,8 @@ struct TriRecord { float4 q0, q1, q2, q3; uint32_t bbox; int npx; };
 
 /* loads triangle `tri` of the view, runs the per-triangle part of tbarycenter/tdraw (main.c:319-324, 344-347)
  * and clips its bbox to the tile */
-__device__ __forceinline__ TriRecord make_record(const RasterParams& p, const float4* xf, uint32_t tri, int px0, int py0, int px1, int py1)
+__device__ __forceinline__ TriRecord make_record(const float4& a, const float4& b, const float4& c, uint32_t tri, int px0, int py0, int px1, int py1)
 {
-    const float4 a = __ldg(xf + __ldg(p.i0 + tri)), b = __ldg(xf + __ldg(p.i1 + tri)), c = __ldg(xf + __ldg(p.i2 + tri));
     const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
     const int bx0 = max(s.x0, px0) - px0, bx1 = min(s.x1, px1) - px0;
     const int by0 = max(s.y0, py0) - py0, by1 = min(s.y1, py1) - py0;
@@ -371,6 +342,31 @@ __device__ __forceinline__ TriRecord make_record(const RasterParams& p, const fl
     r.q3 = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
     r.bbox = (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15 | (guard ? 1u << 20 : 0u);
     return r;
+}
+
+/* Two-phase depth culling (exact): a tile's triangles are split at zthr = midpoint of the range of their max
+ * vertex z (from K2).  The near ones are rasterised first; the far ones are parked as 16-byte records
+ * (triangle, tile-local bbox, depth bound) in the CTA's scratch.  Then hiz[] = per 8x8 block the minimum depth
+ * key over its pixels, and a far triangle whose every fragment is provably below that -- z <= zmax*(1+7ulp)
+ * < bound, and bound < the minimum of every block its bbox touches, strictly -- can never pass main.c:356
+ * and is dropped without being set up. */
+__device__ __forceinline__ uint32_t clipped_bbox(const float4& a, const float4& b, const float4& c, int px0, int py0, int px1, int py1, bool& any)
+{
+    const int bx0 = max(gel::trunc_i(fminf(a.x, fminf(b.x, c.x))), px0) - px0, bx1 = min(gel::trunc_i(fmaxf(a.x, fmaxf(b.x, c.x))), px1) - px0;
+    const int by0 = max(gel::trunc_i(fminf(a.y, fminf(b.y, c.y))), py0) - py0, by1 = min(gel::trunc_i(fmaxf(a.y, fmaxf(b.y, c.y))), py1) - py0;
+    any = bx0 <= bx1 && by0 <= by1;
+    return (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15;
+}
+
+__device__ __forceinline__ uint32_t depth_bound_key(float zmax) { return gel::zkey(zmax + fabsf(zmax) * 1e-5f + 1e-37f); }
+
+/* true when the parked triangle cannot be culled */
+__device__ __forceinline__ bool survives_hiz(const RasterSmem& sm, uint32_t bbox, uint32_t bound)
+{
+    const int gx0 = (bbox & 31) >> 3, gx1 = ((bbox >> 5) & 31) >> 3, gy0 = ((bbox >> 10) & 31) >> 3, gy1 = ((bbox >> 15) & 31) >> 3;
+    if(gx1 - gx0 > 1 || gy1 - gy0 > 1) return true;           /* spans more than 2x2 blocks: not worth testing */
+    const uint32_t lowest = min(min(sm.hiz[gx0 * 4 + gy0], sm.hiz[gx0 * 4 + gy1]), min(sm.hiz[gx1 * 4 + gy0], sm.hiz[gx1 * 4 + gy1]));
+    return !(bound < lowest);
 }
 
 /* Cheap tests that are EXACT rejections of main.c:352 (den > 0 after normalisation):
@@ -403,8 +399,54 @@ __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
 
+/* reset (main.c:413-417) of a tile no triangle touches: pure HBM stores, one warp per tile.  The rasteriser CTAs
+ * issue these fire-and-forget stores between their work items, so they overlap the instruction-bound raster work. */
 template<bool HASH>
-__global__ void __launch_bounds__(RASTER_THREADS, 4)
+__device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int g, int lane)
+{
+    if(g >= p.ntiles * p.nviews || __ldg(p.tile_lit + g)) return;
+    const int view = g / p.ntiles, tile = g - view * p.ntiles;
+    const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
+    const int px0 = tx * TW, py0 = ty * TH;
+    const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
+    uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
+    float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
+    if(!HASH && (p.yres & 3) == 0 && py1 - py0 + 1 == TH)
+    {
+        /* 8 lanes x 16 B = one 128-byte column of the tile; 4 columns per store instruction */
+        const int y = py0 + (lane & 7) * 4;
+        #pragma unroll
+        for(int k = 0; k < TW / 4; k++)
+        {
+            const int x = px0 + k * 4 + (lane >> 3);
+            if(x <= px1)
+            {
+                const size_t idx = (size_t) y + (size_t) x * p.yres;
+                *reinterpret_cast<uint4*>(pixel + idx) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<float4*>(zbuf + idx) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            }
+        }
+        return;
+    }
+    unsigned long long hp = 0, hz = 0;
+    const int y = py0 + lane;
+    if(y <= py1)
+        for(int x = px0; x <= px1; x++)
+        {
+            const int idx = y + x * p.yres;
+            pixel[idx] = 0u;
+            zbuf[idx] = -FLT_MAX;
+            if(HASH) { hp += gel::salt_mix(0u, (uint32_t) idx); hz += gel::salt_mix(0xFF7FFFFFu, (uint32_t) idx); }
+        }
+    if(HASH)
+    {
+        for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+        if(lane == 0) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
+    }
+}
+
+template<bool HASH>
+__global__ void __launch_bounds__(RASTER_THREADS, 1024 / RASTER_THREADS)
 raster_kernel(RasterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -414,23 +456,27 @@ raster_kernel(RasterParams p)
     WarpScratch& ws = sm.ws[warp];
 
     /* work list = the lit tiles of every view, view-major: prefix of the per-view counts K2 left in cursors[view][2] */
+    if(warp == 0)
     {
-        const int c = tid < p.nviews ? __ldg(p.cursors + 4 * tid + 2) : 0;
-        int incl = c;
-        for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
-        if(lane == 31) sm.warp_sums[warp] = incl;
-        __syncthreads();
-        int wbase = 0;
-        for(int w = 0; w < warp; w++) wbase += sm.warp_sums[w];
-        sm.view_pre[tid] = wbase + incl - c;
-        if(tid == RASTER_THREADS - 1) sm.view_pre[MAX_BATCH] = wbase + incl;
-        __syncthreads();
+        int run = 0;
+        for(int base = 0; base < MAX_BATCH; base += 32)
+        {
+            const int v = base + lane;
+            const int c = v < p.nviews ? __ldg(p.cursors + 4 * v + 2) : 0;
+            int incl = c;
+            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+            sm.view_pre[v] = run + incl - c;
+            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if(lane == 0) sm.view_pre[MAX_BATCH] = run;
     }
+    __syncthreads();
     const int nitems = sm.view_pre[MAX_BATCH];
 
     /* thread 0 owns the work queue: the atomic for the NEXT item is issued when the current tile starts and its
      * result is only consumed after the tile's visibility pass, so the round trip hides behind real work */
-    int nx_view = -1, nx_tile = 0, g_next = 0;
+    int nx_view = -1, nx_tile = 0, g_next = 0, c_next = 0;
+    const int nclear = p.ntiles * p.nviews;
     auto locate = [&](int g) {
         nx_view = -1;
         if(g < nitems)
@@ -442,13 +488,13 @@ raster_kernel(RasterParams p)
             nx_tile = __ldg(p.lit_list + (size_t) lo * p.ntiles + (g - sm.view_pre[lo]));
         }
     };
-    if(tid == 0) locate(atomicAdd(p.work_counter, 1));
+    if(tid == 0) { locate(atomicAdd(p.work_counter, 1)); c_next = atomicAdd(p.work_counter + 1, CLEAR_CHUNK); }
 
     for(;;)
     {
         if(tid == 0)
         {
-            sm.it_view = nx_view; sm.it_tile = nx_tile;
+            sm.it_view = nx_view; sm.it_tile = nx_tile; sm.it_clear = c_next;
             const int tx = nx_tile / p.tiles_y;
             sm.it_tx = tx; sm.it_ty = nx_tile - tx * p.tiles_y;
             sm.hash[0] = 0; sm.hash[1] = 0;
@@ -456,7 +502,8 @@ raster_kernel(RasterParams p)
         __syncthreads();
         const int view = sm.it_view;
         if(view < 0) break;
-        if(tid == 0) g_next = atomicAdd(p.work_counter, 1);
+        if(tid == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, CLEAR_CHUNK); }
+        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, sm.it_clear + j, lane);
         const int tile = sm.it_tile;
         const int px0 = sm.it_tx * TW, py0 = sm.it_ty * TH;
         const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
@@ -467,150 +514,122 @@ raster_kernel(RasterParams p)
         const uint32_t* entries = p.entries + (size_t) view * p.cap_e;
         unsigned long long hp = 0, hz = 0;
 
-        if(tid < NCHAIN) sm.chain[tid] = __ldg(p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + tid);
+        if(tid == 0)
+        {
+            const float lo = gel::zkey_inv(__ldg(p.zrange + 2 * view)), hi = gel::zkey_inv(__ldg(p.zrange + 2 * view + 1));
+            sm.zthr = lo + 0.5f * (hi - lo);
+            sm.nfar = 0;
+        }
+        if(tid < 16) sm.hiz[tid] = 0xFFFFFFFFu;
         for(int i = tid; i < TW * TH; i += RASTER_THREADS) sm.keys[i] = CLEAR_KEY;
 
         /* ================= visibility: every (triangle, pixel) of main.c:348-356 inside this tile ================= */
-        for(;;)
-        {
-            /* ---- stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) ---- */
-            if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
-            __syncthreads();
-            if(tid < NCHAIN)
-            {
-                int cur = sm.chain[tid], k = 0;
-                while(cur >= 0 && k < SEG_SLOTS / NCHAIN)
-                {
-                    const uint4 d = __ldg(descs + cur);
-                    sm.seg_first[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.y;
-                    sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.z;      /* size for now */
-                    cur = (int) d.x; k++;
-                }
-                for(; k < SEG_SLOTS / NCHAIN; k++) sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = 0;
-                sm.chain[tid] = cur;
-            }
-            const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
-            const int my_count = sm.seg_pre[tid];
-            int incl = my_count;
-            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
-            if(lane == 31) sm.warp_sums[warp] = incl;
-            __syncthreads();
-            int wbase = 0, round_entries = 0;
-            #pragma unroll
-            for(int w = 0; w < RASTER_WARPS; w++) { const int x = sm.warp_sums[w]; if(w < warp) wbase += x; round_entries += x; }
-            sm.seg_pre[tid] = wbase + incl - my_count;
-            __syncthreads();
+        uint4* far_rec = p.far_scratch + (size_t) blockIdx.x * FAR_CAP;
 
-            /* ---- small triangles: every warp pulls 32 entries at a time, no CTA barrier inside ---- */
-            int qn = 0;                                                   /* survivors on the warp's stack (warp-uniform) */
-            for(;;)
+        /* One warp, 32 candidate triangles (have / tri / a,b,c per lane) -> column units -> rows -> survivors -> keys.
+         * Triangles too large for the unit path are left in sm.defer for the CTA-wide sweep. */
+        int qn = 0;                                                       /* survivors on the warp's stack (warp-uniform) */
+        auto rasterise_batch = [&](bool have, uint32_t tri, const float4& a, const float4& b, const float4& c)
+        {
+            int nun = 0, x = 0;
+            if(have)
             {
-                int e0 = 0;
-                if(lane == 0) e0 = atomicAdd(&sm.next_entry, 32);
-                e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
-                if(e0 >= round_entries) break;
-                const int e = e0 + lane;
-                int nun = 0, x = 0;
-                if(e < round_entries)
+                const TriRecord r = make_record(a, b, c, tri, px0, py0, px1, py1);
+                bool unitised = r.npx > 0;
+                if(r.npx > FRAG_MAX)
                 {
-                    /* staged segment holding entry e: last slot with seg_pre <= e */
-                    int lo = 0;
-                    #pragma unroll
-                    for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
-                    const int pool = sm.seg_first[lo] + (e - sm.seg_pre[lo]);
-                    const TriRecord r = make_record(p, xf, __ldg(entries + pool), px0, py0, px1, py1);
-                    bool unitised = r.npx > 0;
-                    if(r.npx > FRAG_MAX)
-                    {
-                        const int slot = atomicAdd(&sm.ndefer, 1);
-                        if(slot < DEFER_MAX) { sm.defer[slot] = pool; unitised = false; }
-                    }
-                    if(unitised)
-                    {
-                        x = r.bbox & 31;
-                        nun = (int) ((r.bbox >> 5) & 31) - x + 1;             /* one unit per bbox column */
-                        ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
-                        ws.bbox[lane] = r.bbox;
-                        ws.den_hi[lane] = r.q2.w * U_SLACK;
-                    }
+                    const int slot = atomicAdd(&sm.ndefer, 1);
+                    if(slot < DEFER_MAX) { sm.defer[slot] = (int) tri; unitised = false; }
                 }
-                int uincl = nun;
-                for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
-                const int ustart = uincl - nun;
-                const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
-                int emitted = 0;
-                __syncwarp();
-                for(int w0 = 0; w0 < utotal; w0 += UNIT_WINDOW)
+                if(unitised)
                 {
-                    /* expansion: one 16-bit word per column unit */
-                    while(emitted < nun && ustart + emitted < w0 + UNIT_WINDOW)
+                    x = r.bbox & 31;
+                    nun = (int) ((r.bbox >> 5) & 31) - x + 1;                 /* one unit per bbox column */
+                    ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
+                    ws.bbox[lane] = r.bbox;
+                    ws.den_hi[lane] = r.q2.w * U_SLACK;
+                }
+            }
+            int uincl = nun;
+            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
+            const int ustart = uincl - nun;
+            const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
+            int emitted = 0;
+            __syncwarp();
+            for(int w0 = 0; w0 < utotal; w0 += UNIT_WINDOW)
+            {
+                /* expansion: one 16-bit word per column unit */
+                while(emitted < nun && ustart + emitted < w0 + UNIT_WINDOW)
+                {
+                    ws.unit[ustart + emitted - w0] = (unsigned short) (lane << 5 | (x + emitted));
+                    emitted++;
+                }
+                __syncwarp();
+                const int n = min(UNIT_WINDOW, utotal - w0);
+                for(int u0 = 0; u0 < n; u0 += 32)
+                {
+                    /* stage 1: numerators of v and w (main.c:325-328) down the column; exact cheap rejections */
+                    const bool act = u0 + lane < n;
+                    const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
+                    const int src = o >> 5, xl = o & 31;
+                    const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
+                    const uint32_t bb = ws.bbox[src];
+                    const float den_hi = ws.den_hi[src];
+                    const int y0l = (bb >> 10) & 31;
+                    const int rows = act ? (int) ((bb >> 15) & 31) - y0l + 1 : 0;
+                    const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
+                    const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
+                    const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                    const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
+                    float fy = gel::i2f(py0 + y0l);
+                    uint32_t id = (uint32_t) src << 10 | (uint32_t) xl << 5 | (uint32_t) y0l;
+                    for(int r = 0; r < maxrows; r++, id++)
                     {
-                        ws.unit[ustart + emitted - w0] = (unsigned short) (lane << 5 | (x + emitted));
-                        emitted++;
-                    }
-                    __syncwarp();
-                    const int n = min(UNIT_WINDOW, utotal - w0);
-                    for(int u0 = 0; u0 < n; u0 += 32)
-                    {
-                        /* stage 1: numerators of v and w (main.c:325-328) down the column; exact cheap rejections */
-                        const bool act = u0 + lane < n;
-                        const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
-                        const int src = o >> 5, xl = o & 31;
-                        const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
-                        const uint32_t bb = ws.bbox[src];
-                        const float den_hi = ws.den_hi[src];
-                        const int y0l = (bb >> 10) & 31;
-                        const int rows = act ? (int) ((bb >> 15) & 31) - y0l + 1 : 0;
-                        const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
-                        const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                        const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
-                        const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
-                        float fy = gel::i2f(py0 + y0l);
-                        uint32_t id = (uint32_t) src << 10 | (uint32_t) xl << 5 | (uint32_t) y0l;
-                        for(int r = 0; r < maxrows; r++, id++)
+                        const float v2y = gel::sub(fy, q0.y);
+                        fy = gel::add(fy, 1.0f);                              /* exact: small integers */
+                        const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
+                        const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
+                        const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                        const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                        const bool pass = r < rows && may_be_inside(nv, nw, eps, den_hi);
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                        if(pass)
                         {
-                            const float v2y = gel::sub(fy, q0.y);
-                            fy = gel::add(fy, 1.0f);                          /* exact: small integers */
-                            const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
-                            const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
-                            const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
-                            const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                            const bool pass = r < rows && may_be_inside(nv, nw, eps, den_hi);
-                            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-                            if(pass)
-                            {
-                                const int slot = qn + __popc(m & lt_mask);
-                                ws.q_id[slot] = (unsigned short) id;
-                                ws.q_n[slot] = make_float2(nv, nw);
-                            }
-                            qn += __popc(m);
-                            if(qn >= 32)
-                            {
-                                /* stage 2: divisions, inside test, depth, key -- a full warp off the top of the stack */
-                                __syncwarp();
-                                qn -= 32;
-                                resolve_survivor(sm, ws, qn + lane);
-                                __syncwarp();
-                            }
+                            const int slot = qn + __popc(m & lt_mask);
+                            ws.q_id[slot] = (unsigned short) id;
+                            ws.q_n[slot] = make_float2(nv, nw);
+                        }
+                        qn += __popc(m);
+                        if(qn >= 32)
+                        {
+                            /* stage 2: divisions, inside test, depth, key -- a full warp off the top of the stack */
+                            __syncwarp();
+                            qn -= 32;
+                            resolve_survivor(sm, ws, qn + lane);
+                            __syncwarp();
                         }
                     }
-                    __syncwarp();
                 }
                 __syncwarp();
-                if(lane < qn) resolve_survivor(sm, ws, lane);
-                qn = 0;
-                __syncwarp();
             }
-            __syncthreads();
+            __syncwarp();
+            if(lane < qn) resolve_survivor(sm, ws, lane);
+            qn = 0;
+            __syncwarp();
+        };
 
-            /* ---- large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, ..,
-             *      lane = row, so every pixel has exactly one owner thread and no atomics are needed ---- */
+        /* large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, .., lane = row,
+         * so every pixel has exactly one owner thread and no atomics are needed */
+        auto sweep_deferred = [&]()
+        {
             const int ndefer = min(sm.ndefer, DEFER_MAX);
             for(int base = 0; base < ndefer; base += RASTER_THREADS)
             {
                 if(base + tid < ndefer)
                 {
-                    const TriRecord r = make_record(p, xf, __ldg(entries + sm.defer[base + tid]), px0, py0, px1, py1);
+                    const uint32_t tri = (uint32_t) sm.defer[base + tid];
+                    const float4 a = __ldg(xf + __ldg(p.i0 + tri)), b = __ldg(xf + __ldg(p.i1 + tri)), c = __ldg(xf + __ldg(p.i2 + tri));
+                    const TriRecord r = make_record(a, b, c, tri, px0, py0, px1, py1);
                     ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
                     ws.bbox[lane] = r.bbox;
                 }
@@ -643,9 +662,146 @@ raster_kernel(RasterParams p)
                 }
                 __syncthreads();
             }
+        };
+
+        /* ---------------- phase 0: walk the tile's segments; near triangles are rasterised, far ones parked ---------------- */
+        if(tid < NCHAIN) sm.chain[tid] = __ldg(p.heads + ((size_t) view * p.ntiles + tile) * NCHAIN + tid);
+        bool first_round = true;
+        float zthr = 0.0f;
+        for(;;)
+        {
+            /* stage up to SEG_SLOTS segments: chain c fills slots [c*32, c*32+32) */
+            if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
+            __syncthreads();
+            if(tid < NCHAIN)
+            {
+                int cur = sm.chain[tid], k = 0;
+                while(cur >= 0 && k < SEG_SLOTS / NCHAIN)
+                {
+                    const uint4 d = __ldg(descs + cur);
+                    sm.seg_first[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.y;
+                    sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = (int) d.z;      /* size for now */
+                    cur = (int) d.x; k++;
+                }
+                for(; k < SEG_SLOTS / NCHAIN; k++) sm.seg_pre[tid * (SEG_SLOTS / NCHAIN) + k] = 0;
+                sm.chain[tid] = cur;
+            }
+            const int more = __syncthreads_or(tid < NCHAIN && sm.chain[tid] >= 0);
+            const int my_count = sm.seg_pre[tid];
+            int incl = my_count;
+            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
+            if(lane == 31) sm.warp_sums[warp] = incl;
+            __syncthreads();
+            int wbase = 0, round_entries = 0;
+            #pragma unroll
+            for(int w = 0; w < RASTER_WARPS; w++) { const int x = sm.warp_sums[w]; if(w < warp) wbase += x; round_entries += x; }
+            sm.seg_pre[tid] = wbase + incl - my_count;
+            if(first_round)
+            {
+                /* short lists are not worth a second phase: everything is "near" */
+                zthr = (!more && round_entries < TWO_PHASE_MIN) ? -INFINITY : sm.zthr;
+                first_round = false;
+            }
+            __syncthreads();
+
+            for(;;)                                                       /* every warp pulls GRAB entries at a time */
+            {
+                int e0 = 0;
+                if(lane == 0) e0 = atomicAdd(&sm.next_entry, GRAB);
+                e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+                if(e0 >= round_entries) break;
+                #pragma unroll 1
+                for(int half = 0; half < GRAB / 32; half++)
+                {
+                    const int e = e0 + half * 32 + lane;
+                    bool have = false, park = false;
+                    uint32_t tri = 0, bbox = 0, bound = 0;
+                    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+                    if(e < round_entries)
+                    {
+                        /* staged segment holding entry e: last slot with seg_pre <= e */
+                        int lo = 0;
+                        #pragma unroll
+                        for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
+                        tri = __ldg(entries + sm.seg_first[lo] + (e - sm.seg_pre[lo]));
+                        a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                        const float zmax = fmaxf(a.z, fmaxf(b.z, c.z));
+                        have = true;
+                        if(zmax < zthr)                                   /* NaN compares false: near */
+                        {
+                            bool any;
+                            bbox = clipped_bbox(a, b, c, px0, py0, px1, py1, any);
+                            bound = depth_bound_key(zmax);
+                            park = any; have = false;
+                        }
+                    }
+                    const unsigned pm = __ballot_sync(0xFFFFFFFFu, park);
+                    if(pm)
+                    {
+                        int base = 0;
+                        if(lane == 0) base = atomicAdd(&sm.nfar, __popc(pm));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if(park)
+                        {
+                            const int slot = base + __popc(pm & lt_mask);
+                            if(slot < FAR_CAP) far_rec[slot] = make_uint4(tri, bbox, bound, 0u);
+                            else have = true;                             /* scratch full: rasterise it now */
+                        }
+                    }
+                    rasterise_batch(have, tri, a, b, c);
+                }
+            }
+            __syncthreads();
+            sweep_deferred();
             if(!more) break;
         }
         __syncthreads();
+
+        /* ---------------- phase 1: the parked triangles against the hierarchical depth of what is already drawn ---------------- */
+        const int nfar = min(sm.nfar, FAR_CAP);
+        if(nfar > 0)
+        {
+            /* hiz: a warp reads column x (lane = row); block = (x/8)*4 + lane/8 */
+            for(int x = warp; x < TW; x += RASTER_WARPS)
+            {
+                uint32_t zk = (uint32_t) (sm.keys[x * TH + lane] >> 32);
+                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 1));
+                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 2));
+                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 4));
+                if((lane & 7) == 0) atomicMin(&sm.hiz[(x >> 3) * 4 + (lane >> 3)], zk);
+            }
+            if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
+            __syncthreads();                                              /* hiz complete, far_rec visible to the whole CTA */
+            for(;;)
+            {
+                int e0 = 0;
+                if(lane == 0) e0 = atomicAdd(&sm.next_entry, GRAB);
+                e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+                if(e0 >= nfar) break;
+                #pragma unroll 1
+                for(int half = 0; half < GRAB / 32; half++)
+                {
+                    const int e = e0 + half * 32 + lane;
+                    bool have = false;
+                    uint32_t tri = 0;
+                    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+                    if(e < nfar)
+                    {
+                        const uint4 rec = far_rec[e];
+                        if(survives_hiz(sm, rec.y, rec.z))
+                        {
+                            tri = rec.x;
+                            a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                            have = true;
+                        }
+                    }
+                    if(__any_sync(0xFFFFFFFFu, have)) rasterise_batch(have, tri, a, b, c);
+                }
+            }
+            __syncthreads();
+            sweep_deferred();
+            __syncthreads();
+        }
         if(tid == 0) locate(g_next);
 
         /* ================= shade the winner of every pixel once (main.c:358-366), write the tile back ================= */
@@ -691,6 +847,15 @@ raster_kernel(RasterParams p)
             if(tid == 0) { atomicAdd(p.hash + 2 * view, sm.hash[0]); atomicAdd(p.hash + 2 * view + 1, sm.hash[1]); }
         }
         __syncthreads();
+    }
+    /* no lit tile left: finish the chunk already reserved, then drain the reset queue */
+    for(int base = sm.it_clear; base < nclear; )
+    {
+        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, base + j, lane);
+        __syncthreads();
+        if(tid == 0) sm.it_clear = atomicAdd(p.work_counter + 1, CLEAR_CHUNK);
+        __syncthreads();
+        base = sm.it_clear;
     }
 }
 

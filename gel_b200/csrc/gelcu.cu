@@ -4,6 +4,7 @@
  * Replaces /root/reference main.c:505-522 (reset, per-triangle transform, tdraw) for batches of views.
  * Per batch of B views, all on one stream with no host sync inside:
  *     memset heads/cursors/flags -> K1 transform_kernel -> K2 bin_kernel -> K3 raster_kernel
+ * (K3 also resets the tiles no triangle touched, as background stores between its work items).
  * Frames are double-buffered in HBM so the device->host copy of batch b overlaps the kernels of batch b+1.
  */
 #include "gel_kernels.cuh"
@@ -40,20 +41,20 @@ template<typename T> void dfree(T*& p) { if(p) cudaFree(p); p = nullptr; }
 struct gelcu_ctx
 {
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, clear_stream = nullptr;
-    cudaEvent_t bin_done = nullptr, clear_done = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr;
     /* texture */
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
-    int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 4, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr;
+    int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 1024 / RASTER_THREADS, stage_timing = 1;
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_zrange = nullptr; uint4* d_far = nullptr;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; int hcap = 0;
+    uint32_t* h_zinit = nullptr;   /* pinned {0xFFFFFFFF, 0} x MAX_BATCH: initial per-view depth range */
     std::vector<cudaEvent_t> ev;   /* 4 per batch */
     cudaEvent_t render_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
     int last_batch_views = 0, last_buf = 0;
@@ -64,7 +65,7 @@ namespace {
 
 void free_work(gelcu_ctx* c)
 {
-    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list);
+    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_zrange); dfree(c->d_far);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]);
     c->batch = 0; c->cap_e = 0; c->cap_d = 0;
@@ -88,9 +89,11 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
     CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
     CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
     CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
+    CU(cudaMalloc(&c->d_zrange, sizeof(uint32_t) * 2 * B));
+    CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
     CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
     CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
-    CU(cudaMalloc(&c->d_work, sizeof(int)));
+    CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
     for(int k = 0; k < 2; k++)
     {
         CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
@@ -114,13 +117,14 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
     CU(cudaMemsetAsync(c->d_heads, 0xFF, sizeof(int) * (size_t) n * c->ntiles * NCHAIN, s));
     CU(cudaMemsetAsync(c->d_cursors, 0, sizeof(int) * 4 * n, s));
     CU(cudaMemsetAsync(c->d_tile_lit, 0, sizeof(int) * (size_t) n * c->ntiles, s));
+    CU(cudaMemcpyAsync(c->d_zrange, c->h_zinit, sizeof(uint32_t) * 2 * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t) * n, s));
-    CU(cudaMemsetAsync(c->d_work, 0, sizeof(int), s));
+    CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(int), s));
     if(want_hash) CU(cudaMemsetAsync(c->d_hash, 0, sizeof(unsigned long long) * 2 * n, s));
     CU(cudaEventRecord(ev4[0], s));
     if(c->nuniq > 0)
     {
-        transform_kernel<<<dim3((c->nuniq + 255) / 256, n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->nuniq, c->xres, c->yres);
+        transform_kernel<<<dim3((c->nuniq + 255) / 256, n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->d_zrange, c->nuniq, c->xres, c->yres);
         c->stats.kernels_launched++;
     }
     CU(cudaEventRecord(ev4[1], s));
@@ -132,27 +136,13 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
         c->stats.kernels_launched++;
     }
     CU(cudaEventRecord(ev4[2], s));
-    /* K3a on its own stream: untouched tiles are plain HBM stores and overlap the instruction-bound rasteriser */
-    CU(cudaEventRecord(c->bin_done, s));
-    CU(cudaStreamWaitEvent(c->clear_stream, c->bin_done, 0));
-    {
-        const int warps = n * c->ntiles, blocks = (warps + 7) / 8;
-        if(want_hash) clear_kernel<true><<<blocks, 256, 0, c->clear_stream>>>(c->d_tile_lit, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->ntiles, c->tiles_y, c->xres, c->yres, n);
-        else clear_kernel<false><<<blocks, 256, 0, c->clear_stream>>>(c->d_tile_lit, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->ntiles, c->tiles_y, c->xres, c->yres, n);
-        c->stats.kernels_launched++;
-    }
-    CU(cudaEventRecord(c->clear_done, c->clear_stream));
-    RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list,
+    RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_zrange, c->d_far,
                         c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
                         c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
-    const int grid = c->num_sms * c->ctas_per_sm;
-    if(c->ntri > 0)
-    {
-        if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-        else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-        c->stats.kernels_launched++;
-    }
-    CU(cudaStreamWaitEvent(s, c->clear_done, 0));
+    const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
+    if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+    else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+    c->stats.kernels_launched++;
     CU(cudaEventRecord(ev4[3], s));
     CU(cudaGetLastError());
     return GELCU_OK;
@@ -221,17 +211,19 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     c->tiles_x = (xres + TW - 1) / TW; c->tiles_y = (yres + TH - 1) / TH; c->ntiles = c->tiles_x * c->tiles_y;
     cudaDeviceProp prop;
     if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    int resident = 0;   /* persistent rasteriser: exactly as many CTAs as fit */
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, raster_kernel<false>, RASTER_THREADS, sizeof(RasterSmem)) == cudaSuccess && resident > 0)
+        c->ctas_per_sm = std::min(resident, 16);
     cudaError_t s1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t s2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->clear_stream, cudaStreamNonBlocking);
-    if(s1 == cudaSuccess) s1 = cudaEventCreateWithFlags(&c->bin_done, cudaEventDisableTiming);
-    if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->clear_done, cudaEventDisableTiming);
     for(int k = 0; k < 2 && s1 == cudaSuccess && s2 == cudaSuccess; k++)
     {
         s1 = cudaEventCreateWithFlags(&c->render_done[k], cudaEventDisableTiming);
         s2 = cudaEventCreateWithFlags(&c->copy_done[k], cudaEventDisableTiming);
     }
     if(s1 != cudaSuccess || s2 != cudaSuccess) { delete c; return fail(GELCU_E_CUDA, "stream/event creation failed"); }
+    if(cudaMallocHost(&c->h_zinit, sizeof(uint32_t) * 2 * MAX_BATCH) != cudaSuccess) { delete c; return fail(GELCU_E_NOMEM, "pinned allocation failed"); }
+    for(int v = 0; v < MAX_BATCH; v++) { c->h_zinit[2 * v] = 0xFFFFFFFFu; c->h_zinit[2 * v + 1] = 0u; }
     *out = c;
     return GELCU_OK;
 }
@@ -325,7 +317,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
 {
     if(!c || !name) return fail(GELCU_E_INVALID, "null argument");
     if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
-    else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 32) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,32]"); c->ctas_per_sm = value; }
+    else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
     return GELCU_OK;
@@ -395,7 +387,6 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         if(pixel_out || z_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
-        CU(cudaStreamSynchronize(c->clear_stream));
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
         for(int v = 0; v < nviews; v++)
@@ -518,13 +509,11 @@ void gelcu_destroy(gelcu_ctx* c)
     dfree(c->d_tex); dfree(c->d_views);
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
+    if(c->h_zinit) cudaFreeHost(c->h_zinit);
     for(cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); }
     if(c->stream) cudaStreamDestroy(c->stream);
     if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if(c->clear_stream) cudaStreamDestroy(c->clear_stream);
-    if(c->bin_done) cudaEventDestroy(c->bin_done);
-    if(c->clear_done) cudaEventDestroy(c->clear_done);
     delete c;
 }
 

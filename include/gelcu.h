@@ -95,7 +95,7 @@ int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out
 
 /* Tunables, by name (returns GELCU_E_INVALID for unknown names):
  *   "batch_views"   views rendered per kernel launch set (default: sized so frames fit ~8 GB)
- *   "raster_ctas_per_sm"   persistent rasteriser CTAs per SM (default 4)
+ *   "raster_ctas_per_sm"   persistent rasteriser CTAs per SM, 1..16 (default: 1024 threads per SM)
  *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1) */
 int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
 int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
