@@ -40,8 +40,8 @@ class GelcuError(RuntimeError):
 class Stats(ctypes.Structure):
     _fields_ = [("kernels_launched", c_uint64), ("views", c_uint64), ("bin_entries", c_uint64),
                 ("unique_vertices", c_uint64), ("triangles", c_uint64), ("h2d_bytes", c_uint64),
-                ("d2h_bytes", c_uint64), ("ms_transform", c_float), ("ms_bin", c_float), ("ms_raster", c_float),
-                ("ms_total", c_float), ("flags", c_uint32), ("batches", c_uint32)]
+                ("d2h_bytes", c_uint64), ("ms_transform", c_float), ("ms_bin", c_float), ("ms_raster", c_float), ("ms_dominant", c_float),
+                ("ms_total", c_float), ("flags", c_uint32), ("batches", c_uint32), ("pipeline", c_uint32), ("reserved", c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1,0 +1,432 @@
+/* gel_direct.cuh -- the DIRECT pipeline: gel's render path for meshes whose triangles cover a few pixels each
+ * (cfg 3: 1 M triangles of ~3 px^2 at 4K).  For such meshes screen-tile binning costs more than the raster work
+ * itself, so warps stream the triangles in submission order and merge fragments straight into a per-view key
+ * buffer in global memory with 64-bit atomic max (resolved in L2), using the same key as the tile pipeline:
+ *     key = zkey(z) << 32 | (0xFFFFFFFF - triangle)         (main.c:356 semantics, see gel_kernels.cuh)
+ *
+ *   D0 direct_clear_kernel    key buffer := "no winner" inside the view's screen bbox (from K1), hi-Z := 0
+ *   D1 direct_raster_kernel<0>  every triangle: near ones (max vertex z >= view midpoint) are rasterised, far ones parked
+ *   D2 direct_hiz_kernel      per 8x8 pixel block: minimum depth key over its pixels
+ *   D3 direct_raster_kernel<1>  parked triangles: dropped when provably behind every block they touch, else rasterised
+ *   D5 direct_resolve_kernel  every pixel of the frame: winner shaded once (main.c:358-366) or reset (main.c:413-417),
+ *                             colour + z written once, coalesced
+ *
+ * The per-pixel arithmetic (numerators, exact cheap rejections, divisions, depth, shading) is shared with the tile
+ * pipeline; only the staging differs.  No CTA-wide barrier is used in D1/D3: each warp owns its scratch.
+ */
+#ifndef GEL_DIRECT_CUH
+#define GEL_DIRECT_CUH
+
+#include "gel_kernels.cuh"
+
+namespace gelk {
+
+constexpr int DIRECT_THREADS = 128;
+constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
+constexpr int DIRECT_TRIS_PER_WARP = 256;          /* consecutive triangles a warp streams through */
+constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
+constexpr int DIRECT_UNIT_WINDOW = 512;
+constexpr int DIRECT_MAX_ROWS = 32;                /* taller (or > FRAG_MAX px) bboxes are swept by the whole warp */
+constexpr int VSTAT = VIEW_STAT_WORDS;             /* per-view words: zlo, zhi, xmin, xmax, ymin, ymax, far count, - */
+
+struct DirectParams
+{
+    const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
+    const uint32_t* tex; int tw, th;
+    unsigned long long* keys;      /* [view][xres*yres]  index y + x*yres                                   */
+    uint32_t* hiz;                 /* [view][hbx*hby]    min depth key per 8x8 block, index bx*hby + by     */
+    uint4* far;                    /* [view][ntri]       parked: tri, x0 | x1 << 16, y0 | y1 << 16, bound; warp w of D1 owns
+                                    *                     records [w*DIRECT_TRIS_PER_WARP, ...) and writes their count to far_count */
+    int* far_count;                /* [view][warps]                                                         */
+    int* region;                   /* [view][REGION_WORDS]  written by D0                                   */
+    uint32_t* vstat;               /* [view][VSTAT]                                                         */
+    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags;
+    int ntri, nuniq, xres, yres, hbx, hby, nviews;
+};
+
+struct DirectScratch               /* per warp */
+{
+    float4 slab[4][32];
+    uint32_t unit[DIRECT_UNIT_WINDOW];   /* lane << 13 | x */
+    float2 q_n[QCAP];
+    uint32_t q_id[QCAP];                 /* lane << 26 | x << 13 | y */
+    uint32_t bx[32], by[32];             /* x0 | x1 << 16 ;  y0 | y1 << 13 | guard << 26 */
+    float den_hi[32];
+};
+
+/* screen bbox of a view's vertices, clipped to the frame and widened to whole 8x8 blocks; false when empty */
+__device__ __forceinline__ bool view_region(const DirectParams& p, int view, int& x0, int& x1, int& y0, int& y1)
+{
+    const uint32_t* s = p.vstat + (size_t) view * VSTAT;
+    x0 = max((int) s[2], 0) & ~7; y0 = max((int) s[4], 0) & ~7;
+    x1 = min(min((int) s[3], p.xres - 1) | 7, p.xres - 1); y1 = min(min((int) s[5], p.yres - 1) | 7, p.yres - 1);
+    return x0 <= x1 && y0 <= y1;
+}
+
+/* the region D0 published for the view; false when empty */
+__device__ __forceinline__ bool load_region(const DirectParams& p, int view, int& x0, int& x1, int& y0, int& y1)
+{
+    const int4 r = __ldg(reinterpret_cast<const int4*>(p.region + (size_t) view * REGION_WORDS));
+    x0 = r.x; x1 = r.y; y0 = r.z; y1 = r.w;
+    return x0 <= x1 && y0 <= y1;
+}
+
+/* D0 ------------------------------------------------------------------------------------------------------------ */
+/* grid (G, nviews): CTA g of a view takes the region's columns x0+g, x0+g+G, ... */
+__global__ void __launch_bounds__(256)
+direct_clear_kernel(DirectParams p)
+{
+    const int view = blockIdx.y;
+    int x0, x1, y0, y1;
+    /* hi-Z defaults to 0 (= nothing can be culled) everywhere */
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.hbx * p.hby; i += gridDim.x * blockDim.x)
+        p.hiz[(size_t) view * p.hbx * p.hby + i] = 0u;
+    const bool any = view_region(p, view, x0, x1, y0, y1);
+    if(blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        int* r = p.region + (size_t) view * REGION_WORDS;
+        const uint32_t* s = p.vstat + (size_t) view * VSTAT;
+        const float lo = gel::zkey_inv(s[0]), hi = gel::zkey_inv(s[1]);
+        r[0] = any ? x0 : 0; r[1] = any ? x1 : -1; r[2] = any ? y0 : 0; r[3] = any ? y1 : -1;
+        r[4] = __float_as_int(lo + 0.5f * (hi - lo));          /* near / far split of the view */
+    }
+    if(!any) return;
+    for(int x = x0 + blockIdx.x; x <= x1; x += gridDim.x)
+    {
+        unsigned long long* col = p.keys + (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
+        for(int y = y0 + threadIdx.x; y <= y1; y += blockDim.x) col[y] = CLEAR_KEY;
+    }
+}
+
+/* D2 ------------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256)
+direct_hiz_kernel(DirectParams p)
+{
+    const int view = blockIdx.y;
+    int x0, x1, y0, y1;
+    if(!load_region(p, view, x0, x1, y0, y1)) return;
+    const int nbx = (x1 >> 3) - (x0 >> 3) + 1, nby = (y1 >> 3) - (y0 >> 3) + 1;
+    const unsigned long long* keys = p.keys + (size_t) view * p.xres * p.yres;
+    for(int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbx * nby; b += gridDim.x * blockDim.x)
+    {
+        const int bx = (x0 >> 3) + b / nby, by = (y0 >> 3) + b % nby;     /* neighbouring threads: neighbouring rows */
+        uint32_t lowest = 0xFFFFFFFFu;
+        for(int dx = 0; dx < 8; dx++)
+        {
+            const int x = bx * 8 + dx;
+            if(x >= p.xres) break;
+            for(int dy = 0; dy < 8; dy++)
+            {
+                const int y = by * 8 + dy;
+                if(y < p.yres) lowest = min(lowest, (uint32_t) (keys[(size_t) y + (size_t) x * p.yres] >> 32));
+            }
+        }
+        p.hiz[(size_t) view * p.hbx * p.hby + (size_t) bx * p.hby + by] = lowest;
+    }
+}
+
+/* D1 / D3 ------------------------------------------------------------------------------------------------------- */
+
+__device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned long long* keys, DirectScratch& ws, int i)
+{
+    const uint32_t id = ws.q_id[i];
+    const float2 n = ws.q_n[i];
+    const int src = id >> 26, x = (id >> 13) & 8191, y = id & 8191;
+    const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
+    if(key) atomicMax(keys + (size_t) y + (size_t) x * p.yres, key);
+}
+
+template<int PHASE>
+__global__ void __launch_bounds__(DIRECT_THREADS, 8)
+direct_raster_kernel(DirectParams p)
+{
+    __shared__ DirectScratch scratch[DIRECT_WARPS];
+    const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    DirectScratch& ws = scratch[warp];
+    const float4* xf = p.xf + (size_t) view * p.nuniq;
+    unsigned long long* keys = p.keys + (size_t) view * p.xres * p.yres;
+    uint4* far = p.far + (size_t) view * p.ntri;
+    const uint32_t* hiz = p.hiz + (size_t) view * p.hbx * p.hby;
+    const float zthr = PHASE == 0 ? __int_as_float(__ldg(p.region + (size_t) view * REGION_WORDS + 4)) : 0.0f;
+    const int gwarp = blockIdx.x * DIRECT_WARPS + warp, nwarps = gridDim.x * DIRECT_WARPS;
+    const int first = gwarp * DIRECT_TRIS_PER_WARP;
+    if(first >= p.ntri) return;
+    int* my_far_count = p.far_count + (size_t) view * nwarps + gwarp;
+    const int last = PHASE == 0 ? min(first + DIRECT_TRIS_PER_WARP, p.ntri) : first + *my_far_count;
+    int qn = 0, parked = 0;
+    bool clipped = false;
+
+    for(int t0 = first; t0 < last; t0 += 32)
+    {
+        const int t = t0 + lane;
+        bool have = false, park = false;
+        uint32_t tri = 0, pbx = 0, pby = 0, bound = 0;
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        if(t < last)
+        {
+            if(PHASE == 0)
+            {
+                tri = (uint32_t) t;
+                a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                const float zmax = fmaxf(a.z, fmaxf(b.z, c.z));
+                have = true;
+                if(zmax < zthr)                                           /* NaN compares false: near */
+                {
+                    int x0 = gel::trunc_i(fminf(a.x, fminf(b.x, c.x))), x1 = gel::trunc_i(fmaxf(a.x, fmaxf(b.x, c.x)));
+                    int y0 = gel::trunc_i(fminf(a.y, fminf(b.y, c.y))), y1 = gel::trunc_i(fmaxf(a.y, fmaxf(b.y, c.y)));
+                    if(x0 < 0 || y0 < 0 || x1 > p.xres - 1 || y1 > p.yres - 1) { clipped = true; x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, p.xres - 1); y1 = min(y1, p.yres - 1); }
+                    park = x0 <= x1 && y0 <= y1; have = false;
+                    pbx = (uint32_t) x0 | (uint32_t) x1 << 16; pby = (uint32_t) y0 | (uint32_t) y1 << 16;
+                    bound = depth_bound_key(zmax);
+                }
+            }
+            else
+            {
+                const uint4 rec = far[t];
+                const int gx0 = (rec.y & 0xFFFF) >> 3, gx1 = (rec.y >> 16) >> 3, gy0 = (rec.z & 0xFFFF) >> 3, gy1 = (rec.z >> 16) >> 3;
+                bool survive = true;
+                if(gx1 - gx0 <= 1 && gy1 - gy0 <= 1)
+                {
+                    const uint32_t lowest = min(min(__ldg(hiz + gx0 * p.hby + gy0), __ldg(hiz + gx0 * p.hby + gy1)),
+                                                min(__ldg(hiz + gx1 * p.hby + gy0), __ldg(hiz + gx1 * p.hby + gy1)));
+                    survive = !(rec.w < lowest);
+                }
+                if(survive)
+                {
+                    tri = rec.x;
+                    a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                    have = true;
+                }
+            }
+        }
+        if(PHASE == 0)
+        {
+            /* parked triangles are compacted into this warp's own slice of far[] (ballot ranks, no atomics) */
+            const unsigned pm = __ballot_sync(0xFFFFFFFFu, park);
+            if(park) far[first + parked + __popc(pm & lt_mask)] = make_uint4(tri, pbx, pby, bound);
+            parked += __popc(pm);
+        }
+        if(!__any_sync(0xFFFFFFFFu, have)) continue;
+
+        /* ---- per-triangle setup (main.c:319-324, 344-347), bbox clipped to the frame ---- */
+        int nun = 0, ux = 0;
+        bool sweep = false;
+        if(have)
+        {
+            const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+            int x0 = s.x0, y0 = s.y0, x1 = s.x1, y1 = s.y1;
+            if(x0 < 0 || y0 < 0 || x1 > p.xres - 1 || y1 > p.yres - 1) { clipped = true; x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, p.xres - 1); y1 = min(y1, p.yres - 1); }
+            const float ad = fabsf(s.den);
+            const bool drawable = ad > 0.0f && x0 <= x1 && y0 <= y1;     /* den == 0 or NaN can never pass main.c:352 */
+            if(drawable)
+            {
+                const bool guard = ad <= GUARD_DEN_MAX;
+                const float sg = s.den < 0.0f ? -1.0f : 1.0f;
+                ws.slab[0][lane] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
+                ws.slab[1][lane] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
+                ws.slab[2][lane] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
+                ws.slab[3][lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
+                ws.bx[lane] = (uint32_t) x0 | (uint32_t) x1 << 16;
+                ws.by[lane] = (uint32_t) y0 | (uint32_t) y1 << 13 | (guard ? 1u << 26 : 0u);
+                ws.den_hi[lane] = s.den * sg * U_SLACK;
+                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+                sweep = bh > DIRECT_MAX_ROWS || bw * bh > FRAG_MAX;
+                if(!sweep) { nun = bw; ux = x0; }
+            }
+        }
+        __syncwarp();
+
+        /* ---- column units: one lane per bbox column, rows walked with a warp-uniform trip count ---- */
+        int uincl = nun;
+        for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
+        const int ustart = uincl - nun;
+        const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);
+        int emitted = 0;
+        for(int w0 = 0; w0 < utotal; w0 += DIRECT_UNIT_WINDOW)
+        {
+            while(emitted < nun && ustart + emitted < w0 + DIRECT_UNIT_WINDOW)
+            {
+                ws.unit[ustart + emitted - w0] = (uint32_t) lane << 13 | (uint32_t) (ux + emitted);
+                emitted++;
+            }
+            __syncwarp();
+            const int n = min(DIRECT_UNIT_WINDOW, utotal - w0);
+            for(int u0 = 0; u0 < n; u0 += 32)
+            {
+                const bool act = u0 + lane < n;
+                const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
+                const int src = o >> 13, x = o & 8191;
+                const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
+                const uint32_t yy = ws.by[src];
+                const float den_hi = ws.den_hi[src];
+                const int y0 = yy & 8191;
+                const int rows = act ? (int) ((yy >> 13) & 8191) - y0 + 1 : 0;
+                const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
+                const float eps = (yy >> 26) & 1 ? -GUARD_EPS : -INFINITY;
+                const float v2x = gel::sub(gel::i2f(x), q0.x);
+                const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
+                float fy = gel::i2f(y0);
+                uint32_t id = (uint32_t) src << 26 | (uint32_t) x << 13 | (uint32_t) y0;
+                for(int r = 0; r < maxrows; r++, id++)
+                {
+                    const float v2y = gel::sub(fy, q0.y);
+                    fy = gel::add(fy, 1.0f);
+                    const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, q0.w)), q1.z);
+                    const float d21 = gel::add(gel::add(cx1, gel::mul(v2y, q1.y)), q1.w);
+                    const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                    const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                    const bool pass = r < rows && may_be_inside(nv, nw, eps, den_hi);
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                    if(pass)
+                    {
+                        const int slot = qn + __popc(m & lt_mask);
+                        ws.q_id[slot] = id;
+                        ws.q_n[slot] = make_float2(nv, nw);
+                    }
+                    qn += __popc(m);
+                    if(qn >= 32)
+                    {
+                        __syncwarp();
+                        qn -= 32;
+                        direct_resolve(p, keys, ws, qn + lane);
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if(lane < qn) direct_resolve(p, keys, ws, lane);
+        qn = 0;
+        __syncwarp();
+
+        /* ---- triangles too large for the unit path: the whole warp sweeps the bbox, lanes along y ---- */
+        unsigned sm = __ballot_sync(0xFFFFFFFFu, sweep);
+        while(sm)
+        {
+            const int src = __ffs(sm) - 1;
+            sm &= sm - 1;
+            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src], q3 = ws.slab[3][src];
+            const uint32_t xx = ws.bx[src], yy = ws.by[src];
+            const int x0 = xx & 0xFFFF, x1 = xx >> 16, y0 = yy & 8191, y1 = (yy >> 13) & 8191;
+            const float eps = (yy >> 26) & 1 ? -GUARD_EPS : -INFINITY;
+            const float den_hi = ws.den_hi[src];
+            for(int yb = y0; yb <= y1; yb += 32)
+            {
+                const int y = yb + lane;
+                if(y > y1) continue;
+                const float v2y = gel::sub(gel::i2f(y), q0.y);
+                const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
+                for(int x = x0; x <= x1; x++)
+                {
+                    const float v2x = gel::sub(gel::i2f(x), q0.x);
+                    const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
+                    const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                    const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                    const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                    if(!may_be_inside(nv, nw, eps, den_hi)) continue;
+                    const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
+                    if(key) atomicMax(keys + (size_t) y + (size_t) x * p.yres, key);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if(PHASE == 0 && lane == 0) *my_far_count = parked;
+    if(__any_sync(0xFFFFFFFFu, clipped) && lane == 0) atomicOr(p.flags + view, FLAG_CLIPPED);
+}
+
+/* D5 ------------------------------------------------------------------------------------------------------------ */
+/* one pixel: the winner's barycentrics recomputed from the same operands (identical bits), shaded once */
+__device__ __forceinline__ void direct_shade(const DirectParams& p, int view, unsigned long long key, int x, int y, uint32_t& colour, float& z)
+{
+    colour = 0u; z = -FLT_MAX;
+    if(key == CLEAR_KEY) return;
+    const float4* xf = p.xf + (size_t) view * p.nuniq;
+    const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
+    z = gel::zkey_inv((uint32_t) (key >> 32));
+    const float4 a = __ldg(xf + __ldg(p.i0 + tri));
+    const float4 b = __ldg(xf + __ldg(p.i1 + tri));
+    const float4 c = __ldg(xf + __ldg(p.i2 + tri));
+    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+    float nv, nw, v, w, u, zz;
+    gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+    gel::bary_inside(s, nv, nw, v, w, u, zz);
+    const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
+    const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
+    int xx, yy, shading;
+    gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
+    if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
+    {
+        atomicOr(p.flags + view, FLAG_TEXCLAMP);           /* the reference reads out of bounds here (R) */
+        xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
+    }
+    colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+}
+
+/* D5a: reset (main.c:413-417) of everything outside the view's region -- pure stores.
+ * grid (ceil(yres / 1024), xres, nviews): a thread owns 4 consecutive rows of one column (regions are 8-aligned) */
+template<bool HASH>
+__global__ void __launch_bounds__(256)
+direct_fill_kernel(DirectParams p)
+{
+    const int view = blockIdx.z, x = blockIdx.y;
+    const int y4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int rx0, rx1, ry0, ry1;
+    const bool region = load_region(p, view, rx0, rx1, ry0, ry1) && x >= rx0 && x <= rx1;
+    unsigned long long hp = 0, hz = 0;
+    if(y4 < p.yres && !(region && y4 >= ry0 && y4 <= ry1))
+    {
+        const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
+        if((p.yres & 3) == 0)
+        {
+            *reinterpret_cast<uint4*>(p.pixel + base + y4) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<float4*>(p.zbuf + base + y4) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        }
+        for(int k = 0; k < 4; k++)
+        {
+            const int y = y4 + k;
+            if(y >= p.yres || (region && y >= ry0 && y <= ry1)) continue;
+            if((p.yres & 3) != 0) { p.pixel[base + y] = 0u; p.zbuf[base + y] = -FLT_MAX; }
+            if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(0u, idx); hz += gel::salt_mix(0xFF7FFFFFu, idx); }
+        }
+    }
+    if(HASH)
+    {
+        for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+        if((threadIdx.x & 31) == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
+    }
+}
+
+/* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): CTA g takes the region's
+ * columns x0+g, x0+g+G, ...; one thread per pixel so the dependent loads of many pixels are in flight. */
+template<bool HASH>
+__global__ void __launch_bounds__(256)
+direct_resolve_kernel(DirectParams p)
+{
+    const int view = blockIdx.y;
+    int rx0, rx1, ry0, ry1;
+    if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
+    unsigned long long hp = 0, hz = 0;
+    for(int x = rx0 + blockIdx.x; x <= rx1; x += gridDim.x)
+    {
+        const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
+        for(int y = ry0 + threadIdx.x; y <= ry1; y += blockDim.x)
+        {
+            uint32_t colour; float z;
+            direct_shade(p, view, p.keys[base + y], x, y, colour, z);
+            p.pixel[base + y] = colour;
+            p.zbuf[base + y] = z;
+            if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(colour, idx); hz += gel::salt_mix(__float_as_uint(z), idx); }
+        }
+    }
+    if(HASH)
+    {
+        for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+        if((threadIdx.x & 31) == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
+    }
+}
+
+} /* namespace gelk */
+#endif /* GEL_DIRECT_CUH */

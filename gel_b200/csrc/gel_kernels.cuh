@@ -25,6 +25,7 @@
 #include "gel_math.h"
 
 #include <cuda_runtime.h>
+#include <climits>
 
 namespace gelk {
 
@@ -62,31 +63,56 @@ constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f, U_SLACK = 1.00001f;
 /* K1: vertex transform                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
 
+/* per-view statistics K1 leaves for the rasterisers: words 0-1 range of zkey(screen z), 2-5 screen bbox of the
+ * vertices (int min/max of the truncated x and y), 6 parked-triangle counter of the direct pipeline */
+constexpr int VIEW_STAT_WORDS = 8;
+
+constexpr int XF_PER_THREAD = 4;     /* vertices per thread: amortises the per-warp reductions of the view statistics */
+
 __global__ void __launch_bounds__(256)
 transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict__ vpos,
-                 const float4* __restrict__ vnrm, float4* __restrict__ xf, uint32_t* __restrict__ zrange, int nuniq, int xres, int yres)
+                 const float4* __restrict__ vnrm, float4* __restrict__ xf, uint32_t* __restrict__ vstat, int nuniq, int xres, int yres)
 {
     __shared__ uint32_t s_lo, s_hi;
+    __shared__ int s_box[4];
     const int view = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+    if(threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
     __syncthreads();
+    const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    if(i < nuniq)
+    int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+    #pragma unroll
+    for(int k = 0; k < XF_PER_THREAD; k++)
     {
-        const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
-        const float4 p = __ldg(vpos + i);
-        const float4 n = __ldg(vnrm + i);
-        float4 o;
-        gel::transform_corner(c, p.x, p.y, p.z, n.x, n.y, n.z, o.x, o.y, o.z, o.w);
-        xf[(size_t) view * nuniq + i] = o;
-        if(o.z == o.z) lo = hi = gel::zkey(o.z);
+        const int i = (blockIdx.x * XF_PER_THREAD + k) * blockDim.x + threadIdx.x;      /* coalesced float4 loads and stores */
+        if(i < nuniq)
+        {
+            const float4 p = __ldg(vpos + i);
+            const float4 n = __ldg(vnrm + i);
+            float4 o;
+            gel::transform_corner(c, p.x, p.y, p.z, n.x, n.y, n.z, o.x, o.y, o.z, o.w);
+            xf[(size_t) view * nuniq + i] = o;
+            if(o.z == o.z) { const uint32_t zk = gel::zkey(o.z); lo = min(lo, zk); hi = max(hi, zk); }
+            const int ix = gel::trunc_i(o.x), iy = gel::trunc_i(o.y);
+            x0 = min(x0, ix); x1 = max(x1, ix); y0 = min(y0, iy); y1 = max(y1, iy);
+        }
     }
-    /* range of the view's screen depths: the rasteriser splits near / far triangles at its midpoint */
     lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    if((threadIdx.x & 31) == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    x0 = __reduce_min_sync(0xFFFFFFFFu, x0); x1 = __reduce_max_sync(0xFFFFFFFFu, x1);
+    y0 = __reduce_min_sync(0xFFFFFFFFu, y0); y1 = __reduce_max_sync(0xFFFFFFFFu, y1);
+    if((threadIdx.x & 31) == 0)
+    {
+        atomicMin(&s_lo, lo); atomicMax(&s_hi, hi);
+        atomicMin(&s_box[0], x0); atomicMax(&s_box[1], x1); atomicMin(&s_box[2], y0); atomicMax(&s_box[3], y1);
+    }
     __syncthreads();
-    if(threadIdx.x == 0) { atomicMin(zrange + 2 * view, s_lo); atomicMax(zrange + 2 * view + 1, s_hi); }
+    if(threadIdx.x == 0)
+    {
+        uint32_t* s = vstat + (size_t) view * VIEW_STAT_WORDS;
+        atomicMin(s, s_lo); atomicMax(s + 1, s_hi);
+        atomicMin(reinterpret_cast<int*>(s + 2), s_box[0]); atomicMax(reinterpret_cast<int*>(s + 3), s_box[1]);
+        atomicMin(reinterpret_cast<int*>(s + 4), s_box[2]); atomicMax(reinterpret_cast<int*>(s + 5), s_box[3]);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -284,7 +310,7 @@ struct RasterParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
     const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list; const int* tile_lit;
-    const uint32_t* zrange; uint4* far_scratch;
+    const uint32_t* vstat; uint4* far_scratch;
     const uint32_t* tex; int tw, th;
     uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;   /* [0] lit-tile queue, [1] reset queue */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
@@ -516,7 +542,7 @@ raster_kernel(RasterParams p)
 
         if(tid == 0)
         {
-            const float lo = gel::zkey_inv(__ldg(p.zrange + 2 * view)), hi = gel::zkey_inv(__ldg(p.zrange + 2 * view + 1));
+            const float lo = gel::zkey_inv(__ldg(p.vstat + VIEW_STAT_WORDS * view)), hi = gel::zkey_inv(__ldg(p.vstat + VIEW_STAT_WORDS * view + 1));
             sm.zthr = lo + 0.5f * (hi - lo);
             sm.nfar = 0;
         }

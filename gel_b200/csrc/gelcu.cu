@@ -5,9 +5,11 @@
  * Per batch of B views, all on one stream with no host sync inside:
  *     memset heads/cursors/flags -> K1 transform_kernel -> K2 bin_kernel -> K3 raster_kernel
  * (K3 also resets the tiles no triangle touched, as background stores between its work items).
+ * Meshes of tiny triangles take the DIRECT pipeline instead (gel_direct.cuh):
+ *     K1 -> D0 clear keys -> D1 near triangles -> D2 hi-Z -> D3 parked triangles -> D5 resolve/shade.
  * Frames are double-buffered in HBM so the device->host copy of batch b overlaps the kernels of batch b+1.
  */
-#include "gel_kernels.cuh"
+#include "gel_direct.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -49,13 +51,17 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 1024 / RASTER_THREADS, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_zrange = nullptr; uint4* d_far = nullptr;
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr;
+    /* direct pipeline */
+    unsigned long long* d_keys = nullptr; uint32_t* d_hiz = nullptr; uint4* d_parked = nullptr; int *d_far_count = nullptr, *d_region = nullptr; int hbx = 0, hby = 0;
+    int pipeline_opt = 0, pipeline_auto = 1, work_pipeline = 0;   /* 0 auto, 1 tile, 2 direct */
+    double mean_tri_px = 0.0;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; int hcap = 0;
-    uint32_t* h_zinit = nullptr;   /* pinned {0xFFFFFFFF, 0} x MAX_BATCH: initial per-view depth range */
-    std::vector<cudaEvent_t> ev;   /* 4 per batch */
+    uint32_t* h_vinit = nullptr;   /* pinned initial per-view statistics (VIEW_STAT_WORDS each) x MAX_BATCH */
+    std::vector<cudaEvent_t> ev;   /* EV_PER_BATCH per batch */
     cudaEvent_t render_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
     int last_batch_views = 0, last_buf = 0;
     gelcu_stats stats = {};
@@ -65,41 +71,60 @@ namespace {
 
 void free_work(gelcu_ctx* c)
 {
-    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_zrange); dfree(c->d_far);
+    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]);
     c->batch = 0; c->cap_e = 0; c->cap_d = 0;
 }
 
+constexpr int EV_PER_BATCH = 5;   /* start, after K1, after bin/clear, after the dominant raster kernel, end */
+
+int active_pipeline(const gelcu_ctx* c) { return c->pipeline_opt ? c->pipeline_opt : c->pipeline_auto; }
+
 size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
 {
     const size_t frame = (size_t) c->xres * c->yres;
-    return 2 * frame * 8 + (size_t) c->nuniq * 16 + (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * (NCHAIN + 2) * 4 + 64;
+    size_t b = 2 * frame * 8 + (size_t) c->nuniq * 16 + 64;
+    if(active_pipeline(c) == 2) b += frame * 8 + (size_t) c->hbx * c->hby * 4 + (size_t) c->ntri * 16;
+    else b += (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * (NCHAIN + 2) * 4;
+    return b;
 }
 
 int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
 {
-    if(c->batch >= B && c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_xf) return GELCU_OK;
+    const int pipe = active_pipeline(c);
+    if(c->batch >= B && c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_xf && c->work_pipeline == pipe) return GELCU_OK;
     free_work(c);
     const size_t frame = (size_t) c->xres * c->yres;
     CU(cudaMalloc(&c->d_xf, sizeof(float4) * std::max<size_t>(1, (size_t) B * c->nuniq)));
-    CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) B * cap_e)));
-    CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_d)));
-    CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
-    CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
-    CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
-    CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
-    CU(cudaMalloc(&c->d_zrange, sizeof(uint32_t) * 2 * B));
-    CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
+    CU(cudaMalloc(&c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * B));
     CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
     CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
-    CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+    CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
+    if(pipe == 2)
+    {
+        CU(cudaMalloc(&c->d_keys, sizeof(unsigned long long) * B * frame));
+        CU(cudaMalloc(&c->d_hiz, sizeof(uint32_t) * (size_t) B * c->hbx * c->hby));
+        CU(cudaMalloc(&c->d_parked, sizeof(uint4) * std::max<size_t>(1, (size_t) B * c->ntri)));
+        CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP + DIRECT_WARPS + 1)));
+        CU(cudaMalloc(&c->d_region, sizeof(int) * REGION_WORDS * B));
+    }
+    else
+    {
+        CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) B * cap_e)));
+        CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_d)));
+        CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
+        CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
+        CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
+        CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
+        CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+    }
     for(int k = 0; k < 2; k++)
     {
         CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
         CU(cudaMalloc(&c->d_z[k], sizeof(float) * B * frame));
     }
-    c->batch = B; c->cap_e = cap_e; c->cap_d = cap_d;
+    c->batch = B; c->cap_e = cap_e; c->cap_d = cap_d; c->work_pipeline = pipe;
     return GELCU_OK;
 }
 
@@ -110,47 +135,78 @@ int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
     return (int) std::min<size_t>(MAX_BATCH, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));
 }
 
-/* Enqueues K1..K3 for `n` views starting at d_views + first into frame buffer `buf`. */
-int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaEvent_t* ev4)
+/* Enqueues the kernels for `n` views starting at d_views + first into frame buffer `buf`. */
+int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaEvent_t* ev)
 {
     cudaStream_t s = c->stream;
-    CU(cudaMemsetAsync(c->d_heads, 0xFF, sizeof(int) * (size_t) n * c->ntiles * NCHAIN, s));
+    const int pipe = c->work_pipeline;
+    CU(cudaMemcpyAsync(c->d_vstat, c->h_vinit, sizeof(uint32_t) * VIEW_STAT_WORDS * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(c->d_cursors, 0, sizeof(int) * 4 * n, s));
-    CU(cudaMemsetAsync(c->d_tile_lit, 0, sizeof(int) * (size_t) n * c->ntiles, s));
-    CU(cudaMemcpyAsync(c->d_zrange, c->h_zinit, sizeof(uint32_t) * 2 * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t) * n, s));
-    CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(int), s));
     if(want_hash) CU(cudaMemsetAsync(c->d_hash, 0, sizeof(unsigned long long) * 2 * n, s));
-    CU(cudaEventRecord(ev4[0], s));
+    if(pipe != 2)
+    {
+        CU(cudaMemsetAsync(c->d_heads, 0xFF, sizeof(int) * (size_t) n * c->ntiles * NCHAIN, s));
+        CU(cudaMemsetAsync(c->d_tile_lit, 0, sizeof(int) * (size_t) n * c->ntiles, s));
+        CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(int), s));
+    }
+    CU(cudaEventRecord(ev[0], s));
     if(c->nuniq > 0)
     {
-        transform_kernel<<<dim3((c->nuniq + 255) / 256, n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->d_zrange, c->nuniq, c->xres, c->yres);
+        transform_kernel<<<dim3((c->nuniq + 256 * XF_PER_THREAD - 1) / (256 * XF_PER_THREAD), n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->d_vstat, c->nuniq, c->xres, c->yres);
         c->stats.kernels_launched++;
     }
-    CU(cudaEventRecord(ev4[1], s));
-    if(c->ntri > 0)
+    CU(cudaEventRecord(ev[1], s));
+    if(pipe == 2)
     {
-        BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
-                         c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d };
-        bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
+        DirectParams dp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_tex, c->tw, c->th, c->d_keys, c->d_hiz, c->d_parked, c->d_far_count, c->d_region, c->d_vstat,
+                            c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->ntri, c->nuniq, c->xres, c->yres, c->hbx, c->hby, n };
+        const int tris_per_cta = DIRECT_WARPS * DIRECT_TRIS_PER_WARP;
+        const dim3 rgrid((c->ntri + tris_per_cta - 1) / tris_per_cta, n);
+        direct_clear_kernel<<<dim3(64, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
+        CU(cudaEventRecord(ev[2], s));
+        if(c->ntri > 0)
+        {
+            direct_raster_kernel<0><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            CU(cudaEventRecord(ev[3], s));
+            direct_hiz_kernel<<<dim3(32, n), 256, 0, s>>>(dp);
+            direct_raster_kernel<1><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            c->stats.kernels_launched += 3;
+        }
+        else CU(cudaEventRecord(ev[3], s));
+        const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
+        if(want_hash) { direct_fill_kernel<true><<<fgrid, 256, 0, s>>>(dp); direct_resolve_kernel<true><<<dim3(128, n), 256, 0, s>>>(dp); }
+        else { direct_fill_kernel<false><<<fgrid, 256, 0, s>>>(dp); direct_resolve_kernel<false><<<dim3(128, n), 256, 0, s>>>(dp); }
+        c->stats.kernels_launched += 2;
     }
-    CU(cudaEventRecord(ev4[2], s));
-    RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_zrange, c->d_far,
-                        c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
-                        c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
-    const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
-    if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-    else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-    c->stats.kernels_launched++;
-    CU(cudaEventRecord(ev4[3], s));
+    else
+    {
+        if(c->ntri > 0)
+        {
+            BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
+                             c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d };
+            bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
+            c->stats.kernels_launched++;
+        }
+        CU(cudaEventRecord(ev[2], s));
+        RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_vstat, c->d_far,
+                            c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
+                            c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
+        const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
+        if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        c->stats.kernels_launched++;
+        CU(cudaEventRecord(ev[3], s));
+    }
+    CU(cudaEventRecord(ev[4], s));
     CU(cudaGetLastError());
     return GELCU_OK;
 }
 
 int ensure_events(gelcu_ctx* c, int nbatches)
 {
-    while((int) c->ev.size() < 4 * nbatches)
+    while((int) c->ev.size() < EV_PER_BATCH * nbatches)
     {
         cudaEvent_t e; CU(cudaEventCreate(&e)); c->ev.push_back(e);
     }
@@ -209,6 +265,7 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     gelcu_ctx* c = new gelcu_ctx();
     c->device = device; c->xres = xres; c->yres = yres;
     c->tiles_x = (xres + TW - 1) / TW; c->tiles_y = (yres + TH - 1) / TH; c->ntiles = c->tiles_x * c->tiles_y;
+    c->hbx = (xres + 7) / 8; c->hby = (yres + 7) / 8;
     cudaDeviceProp prop;
     if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     int resident = 0;   /* persistent rasteriser: exactly as many CTAs as fit */
@@ -222,8 +279,14 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
         s2 = cudaEventCreateWithFlags(&c->copy_done[k], cudaEventDisableTiming);
     }
     if(s1 != cudaSuccess || s2 != cudaSuccess) { delete c; return fail(GELCU_E_CUDA, "stream/event creation failed"); }
-    if(cudaMallocHost(&c->h_zinit, sizeof(uint32_t) * 2 * MAX_BATCH) != cudaSuccess) { delete c; return fail(GELCU_E_NOMEM, "pinned allocation failed"); }
-    for(int v = 0; v < MAX_BATCH; v++) { c->h_zinit[2 * v] = 0xFFFFFFFFu; c->h_zinit[2 * v + 1] = 0u; }
+    if(cudaMallocHost(&c->h_vinit, sizeof(uint32_t) * VIEW_STAT_WORDS * MAX_BATCH) != cudaSuccess) { delete c; return fail(GELCU_E_NOMEM, "pinned allocation failed"); }
+    for(int v = 0; v < MAX_BATCH; v++)
+    {
+        uint32_t* w = c->h_vinit + VIEW_STAT_WORDS * v;
+        w[0] = 0xFFFFFFFFu; w[1] = 0u;                                     /* depth range        */
+        w[2] = 0x7FFFFFFFu; w[3] = 0x80000000u; w[4] = 0x7FFFFFFFu; w[5] = 0x80000000u;   /* screen bbox (int min/max) */
+        w[6] = 0u; w[7] = 0u;                                              /* parked triangles   */
+    }
     *out = c;
     return GELCU_OK;
 }
@@ -278,6 +341,19 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         }
         idx[cidx % 3][cidx / 3] = found;
     }
+    /* Pipeline choice: mean projected triangle area (model units -> pixels at depth 0: yres/2 px per unit, main.c:290,
+     * 302-314).  Tiny triangles -> direct pipeline; otherwise the tile pipeline. */
+    double area = 0.0;
+    for(int t = 0; t < ntri; t++)
+    {
+        const float* q = tv + 9 * (size_t) t;
+        const double ux = q[3] - q[0], uy = q[4] - q[1], uz = q[5] - q[2], vx = q[6] - q[0], vy = q[7] - q[1], vz = q[8] - q[2];
+        const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+        const double a2 = cx * cx + cy * cy + cz * cz;
+        if(a2 == a2 && a2 < 1e30) area += 0.5 * sqrt(a2);
+    }
+    c->mean_tri_px = ntri > 0 ? area / ntri * (0.5 * c->yres) * (0.5 * c->yres) : 0.0;
+    c->pipeline_auto = (ntri >= 65536 && c->mean_tri_px < 32.0) ? 2 : 1;
     std::vector<float2> uv(ncorner);
     for(size_t cidx = 0; cidx < ncorner; cidx++) uv[cidx] = make_float2(tt[3 * cidx], tt[3 * cidx + 1]);   /* tt.z is never read, main.c:360-361 */
 
@@ -319,6 +395,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
+    else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
     return GELCU_OK;
 }
@@ -375,7 +452,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         {
             const int buf = b & 1, first = b * c->batch, n = std::min(c->batch, nviews - first);
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
-            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, &c->ev[4 * b]); if(rc) return rc;
+            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
             /* small per-batch results ride the render stream (the next batch overwrites their device copies) */
             CU(cudaMemcpyAsync(c->h_cursors + 4 * first, c->d_cursors, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaMemcpyAsync(c->h_flags + first, c->d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -408,17 +485,20 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
             continue;
         }
         float ms = 0.0f, t = 0.0f;
-        CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4 * (nb - 1) + 3]));
+        CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[EV_PER_BATCH * (nb - 1) + 4]));
         c->stats.ms_total = ms;
         if(c->stage_timing)
             for(int b = 0; b < nb; b++)
             {
-                CU(cudaEventElapsedTime(&t, c->ev[4 * b], c->ev[4 * b + 1])); c->stats.ms_transform += t;
-                CU(cudaEventElapsedTime(&t, c->ev[4 * b + 1], c->ev[4 * b + 2])); c->stats.ms_bin += t;
-                CU(cudaEventElapsedTime(&t, c->ev[4 * b + 2], c->ev[4 * b + 3])); c->stats.ms_raster += t;
+                cudaEvent_t* e = &c->ev[EV_PER_BATCH * b];
+                CU(cudaEventElapsedTime(&t, e[0], e[1])); c->stats.ms_transform += t;
+                CU(cudaEventElapsedTime(&t, e[1], e[2])); c->stats.ms_bin += t;
+                CU(cudaEventElapsedTime(&t, e[2], e[4])); c->stats.ms_raster += t;
+                CU(cudaEventElapsedTime(&t, e[2], e[3])); c->stats.ms_dominant += t;
             }
         if(device_ms) *device_ms = ms;
         c->stats.bin_entries = entries;
+        c->stats.pipeline = (uint32_t) c->work_pipeline;
         c->stats.flags = flags & ~FLAG_OVERFLOW;
         if(c->stats.flags) return fail(GELCU_W_CLIPPED, "input left the reference's defined domain (flags 0x%x: 1 = bbox off screen, 2 = texel out of range); clipped", c->stats.flags);
         return GELCU_OK;
@@ -467,7 +547,10 @@ int gelcu_debug_bins(gelcu_ctx* c, const gelcu_view* view, int* counts, int* ent
     int rc = check_ready(c);
     if(rc) return rc;
     if(!view) return fail(GELCU_E_INVALID, "null view");
+    const int keep = c->pipeline_opt;
+    c->pipeline_opt = 1;                                   /* lists only exist in the tile pipeline */
     rc = gelcu_render(c, view, 1, nullptr, nullptr, nullptr, nullptr);
+    c->pipeline_opt = keep;
     if(rc < 0) return rc;
     const int ne = c->h_cursors[0], nd = c->h_cursors[1];
     std::vector<int> heads((size_t) c->ntiles * NCHAIN);
@@ -509,7 +592,7 @@ void gelcu_destroy(gelcu_ctx* c)
     dfree(c->d_tex); dfree(c->d_views);
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
-    if(c->h_zinit) cudaFreeHost(c->h_zinit);
+    if(c->h_vinit) cudaFreeHost(c->h_vinit);
     for(cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); }
     if(c->stream) cudaStreamDestroy(c->stream);

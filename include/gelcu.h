@@ -55,10 +55,13 @@ typedef struct
     uint64_t d2h_bytes;          /* bytes copied device->host by the call (frames, z, checksums)   */
     float    ms_transform;       /* CUDA-event time of the vertex-transform kernels                */
     float    ms_bin;             /* ... of triangle setup + tile binning (count, scan, fill)       */
-    float    ms_raster;          /* ... of the tile rasteriser                                     */
+    float    ms_raster;          /* ... of the raster stage (all its kernels)                      */
+    float    ms_dominant;        /* ... of the dominant kernel alone (raster_kernel / direct_raster_kernel<0>) */
     float    ms_total;           /* first kernel start to last kernel end (no copies)              */
     uint32_t flags;              /* OR of per-view device flags: 1 = bbox clipped, 2 = texel clamped */
     uint32_t batches;            /* view batches the call was split into                           */
+    uint32_t pipeline;           /* 1 = tile pipeline, 2 = direct pipeline (meshes of tiny triangles) */
+    uint32_t reserved;
 }
 gelcu_stats;
 
@@ -96,7 +99,8 @@ int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out
 /* Tunables, by name (returns GELCU_E_INVALID for unknown names):
  *   "batch_views"   views rendered per kernel launch set (default: sized so frames fit ~8 GB)
  *   "raster_ctas_per_sm"   persistent rasteriser CTAs per SM, 1..16 (default: 1024 threads per SM)
- *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1) */
+ *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1)
+ *   "pipeline"      0 = chosen from the mesh (default), 1 = tile pipeline, 2 = direct pipeline */
 int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
 int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
 
