@@ -349,10 +349,17 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float4 a = __ldg(xf + __ldg(p.i0 + tri));
     const float4 b = __ldg(xf + __ldg(p.i1 + tri));
     const float4 c = __ldg(xf + __ldg(p.i2 + tri));
-    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
-    float nv, nw, v, w, u, zz;
-    gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
-    gel::bary_inside(s, nv, nw, v, w, u, zz);
+    /* tbarycenter at this pixel (main.c:316-332), same operations and operands as the visibility pass */
+    const float v0x = gel::sub(b.x, a.x), v0y = gel::sub(b.y, a.y), v0z = gel::sub(b.z, a.z);
+    const float v1x = gel::sub(c.x, a.x), v1y = gel::sub(c.y, a.y), v1z = gel::sub(c.z, a.z);
+    const float d00 = gel::dot3(v0x, v0y, v0z, v0x, v0y, v0z), d01 = gel::dot3(v0x, v0y, v0z, v1x, v1y, v1z), d11 = gel::dot3(v1x, v1y, v1z, v1x, v1y, v1z);
+    const float den = gel::sub(gel::mul(d00, d11), gel::mul(d01, d01));
+    const float v2x = gel::sub(gel::i2f(x), a.x), v2y = gel::sub(gel::i2f(y), a.y), v2z = gel::sub(0.0f, a.z);
+    const float d20 = gel::add(gel::add(gel::mul(v2x, v0x), gel::mul(v2y, v0y)), gel::mul(v2z, v0z));
+    const float d21 = gel::add(gel::add(gel::mul(v2x, v1x), gel::mul(v2y, v1y)), gel::mul(v2z, v1z));
+    const float v = gel::dvd(gel::sub(gel::mul(d11, d20), gel::mul(d01, d21)), den);
+    const float w = gel::dvd(gel::sub(gel::mul(d00, d21), gel::mul(d01, d20)), den);
+    const float u = gel::sub(gel::sub(1.0f, v), w);
     const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
     const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
     int xx, yy, shading;

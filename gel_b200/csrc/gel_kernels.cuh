@@ -34,11 +34,7 @@ constexpr int TH = 32;             /* tile height (screen y, contiguous in memor
 #ifndef GEL_RASTER_THREADS
 #define GEL_RASTER_THREADS 128
 #endif
-#ifndef GEL_GRAB
-#define GEL_GRAB 32
-#endif
 constexpr int RASTER_THREADS = GEL_RASTER_THREADS;
-constexpr int GRAB = GEL_GRAB;        /* entries a warp pulls from the tile's list per queue access (32 or 64) */
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int FRAG_MAX = 256;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
 constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
@@ -322,7 +318,7 @@ struct WarpScratch
     float4 slab[4][32];                 /* 2 KB   per-triangle constants of the warp's current 32 entries            */
     unsigned short unit[UNIT_WINDOW];   /* 1 KB   column unit -> (lane << 5 | x_local)                               */
     float2 q_n[QCAP];                   /* survivors of the cheap tests, waiting for the division stage: (nv, nw)     */
-    unsigned short q_id[QCAP];          /*                                                 lane << 10 | x << 5 | y    */
+    uint32_t q_id[QCAP];                /*                                   triangle slot << 10 | x_local << 5 | y_local */
     uint32_t bbox[32];                  /* clipped tile-local bbox: x0 | x1 << 5 | y0 << 10 | y1 << 15 | guard << 20  */
     float den_hi[32];                   /* den * (1 + 1e-5): above it nv + nw means u < 0 for certain                 */
 };
@@ -427,6 +423,18 @@ __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws
 
 /* reset (main.c:413-417) of a tile no triangle touches: pure HBM stores, one warp per tile.  The rasteriser CTAs
  * issue these fire-and-forget stores between their work items, so they overlap the instruction-bound raster work. */
+/* stage 2 of the CTA-wide sweep: the survivor's triangle record lives in the scratch of the thread that set it up */
+__device__ __forceinline__ void resolve_swept(RasterSmem& sm, WarpScratch& ws, int i)
+{
+    const uint32_t id = ws.q_id[i];
+    const float2 n = ws.q_n[i];
+    const WarpScratch& os = sm.ws[id >> 15];
+    const int src = (id >> 10) & 31;
+    const unsigned long long key = fragment_key(n.x, n.y, os.slab[2][src].w, os.slab[3][src]);
+    unsigned long long* k = sm.keys + (id & 1023);
+    if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
+}
+
 template<bool HASH>
 __device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int g, int lane)
 {
@@ -622,7 +630,7 @@ raster_kernel(RasterParams p)
                         if(pass)
                         {
                             const int slot = qn + __popc(m & lt_mask);
-                            ws.q_id[slot] = (unsigned short) id;
+                            ws.q_id[slot] = id;
                             ws.q_n[slot] = make_float2(nv, nw);
                         }
                         qn += __popc(m);
@@ -644,8 +652,8 @@ raster_kernel(RasterParams p)
             __syncwarp();
         };
 
-        /* large triangles: the whole CTA sweeps one triangle at a time; warp w owns columns w, w+8, .., lane = row,
-         * so every pixel has exactly one owner thread and no atomics are needed */
+        /* large triangles: the whole CTA sweeps one triangle at a time; warp w takes columns w, w+W, .., lane = row;
+         * survivors of the cheap tests are compacted so the divisions run in full warps */
         auto sweep_deferred = [&]()
         {
             const int ndefer = min(sm.ndefer, DEFER_MAX);
@@ -661,15 +669,16 @@ raster_kernel(RasterParams p)
                 }
                 __syncthreads();
                 const int cnt = min(RASTER_THREADS, ndefer - base);
+                int sq = 0;                                               /* survivors on this warp's stack */
                 for(int li = 0; li < cnt; li++)
                 {
                     const WarpScratch& os = sm.ws[li >> 5];
                     const int src = li & 31;
                     const uint32_t bb = os.bbox[src];
                     const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
-                    if(lane < gy0 || lane > gy1) continue;
+                    const bool rowok = lane >= gy0 && lane <= gy1;
                     const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                    const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src], q3 = os.slab[3][src];
+                    const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src];
                     const float den_hi = q2.w * U_SLACK;
                     const float v2y = gel::sub(gel::i2f(py0 + lane), q0.y);
                     const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
@@ -680,12 +689,27 @@ raster_kernel(RasterParams p)
                         const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
                         const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
                         const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                        if(!may_be_inside(nv, nw, eps, den_hi)) continue;
-                        const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
-                        unsigned long long* k = sm.keys + xl * TH + lane;
-                        if(key > *k) *k = key;
+                        const bool pass = rowok && may_be_inside(nv, nw, eps, den_hi);
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                        if(pass)
+                        {
+                            const int slot = sq + __popc(m & lt_mask);
+                            ws.q_id[slot] = (uint32_t) li << 10 | (uint32_t) xl << 5 | (uint32_t) lane;
+                            ws.q_n[slot] = make_float2(nv, nw);
+                        }
+                        sq += __popc(m);
+                        if(sq >= 32)
+                        {
+                            /* divisions, inside test, depth, key for a full warp of survivors */
+                            __syncwarp();
+                            sq -= 32;
+                            resolve_swept(sm, ws, sq + lane);
+                            __syncwarp();
+                        }
                     }
                 }
+                __syncwarp();
+                if(lane < sq) resolve_swept(sm, ws, lane);
                 __syncthreads();
             }
         };
@@ -730,20 +754,21 @@ raster_kernel(RasterParams p)
             }
             __syncthreads();
 
-            for(;;)                                                       /* every warp pulls GRAB entries at a time */
+            /* every warp pulls `grab` entries at a time: 32 for long lists; fewer for short ones so that all the
+             * warps of the CTA get a share (large triangles are split into column units afterwards anyway) */
+            const int grab = max(4, min(32, (round_entries + 2 * RASTER_WARPS - 1) / (2 * RASTER_WARPS)));
+            for(;;)
             {
                 int e0 = 0;
-                if(lane == 0) e0 = atomicAdd(&sm.next_entry, GRAB);
+                if(lane == 0) e0 = atomicAdd(&sm.next_entry, grab);
                 e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
                 if(e0 >= round_entries) break;
-                #pragma unroll 1
-                for(int half = 0; half < GRAB / 32; half++)
                 {
-                    const int e = e0 + half * 32 + lane;
+                    const int e = e0 + lane;
                     bool have = false, park = false;
                     uint32_t tri = 0, bbox = 0, bound = 0;
                     float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-                    if(e < round_entries)
+                    if(lane < grab && e < round_entries)
                     {
                         /* staged segment holding entry e: last slot with seg_pre <= e */
                         int lo = 0;
@@ -801,13 +826,11 @@ raster_kernel(RasterParams p)
             for(;;)
             {
                 int e0 = 0;
-                if(lane == 0) e0 = atomicAdd(&sm.next_entry, GRAB);
+                if(lane == 0) e0 = atomicAdd(&sm.next_entry, 32);
                 e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
                 if(e0 >= nfar) break;
-                #pragma unroll 1
-                for(int half = 0; half < GRAB / 32; half++)
                 {
-                    const int e = e0 + half * 32 + lane;
+                    const int e = e0 + lane;
                     bool have = false;
                     uint32_t tri = 0;
                     float4 a = make_float4(0, 0, 0, 0), b = a, c = a;

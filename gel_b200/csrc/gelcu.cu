@@ -43,7 +43,8 @@ template<typename T> void dfree(T*& p) { if(p) cudaFree(p); p = nullptr; }
 struct gelcu_ctx
 {
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;   /* side: HBM-bound fill overlapping the raster kernels */
+    cudaEvent_t side_go = nullptr, side_done = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr;
@@ -166,6 +167,14 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
         direct_clear_kernel<<<dim3(64, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
         CU(cudaEventRecord(ev[2], s));
+        /* everything outside the view's region is reset by pure stores: on the side stream, under the raster kernels */
+        CU(cudaEventRecord(c->side_go, s));
+        CU(cudaStreamWaitEvent(c->side_stream, c->side_go, 0));
+        const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
+        if(want_hash) direct_fill_kernel<true><<<fgrid, 256, 0, c->side_stream>>>(dp);
+        else direct_fill_kernel<false><<<fgrid, 256, 0, c->side_stream>>>(dp);
+        CU(cudaEventRecord(c->side_done, c->side_stream));
+        c->stats.kernels_launched++;
         if(c->ntri > 0)
         {
             direct_raster_kernel<0><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
@@ -175,10 +184,10 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
             c->stats.kernels_launched += 3;
         }
         else CU(cudaEventRecord(ev[3], s));
-        const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
-        if(want_hash) { direct_fill_kernel<true><<<fgrid, 256, 0, s>>>(dp); direct_resolve_kernel<true><<<dim3(128, n), 256, 0, s>>>(dp); }
-        else { direct_fill_kernel<false><<<fgrid, 256, 0, s>>>(dp); direct_resolve_kernel<false><<<dim3(128, n), 256, 0, s>>>(dp); }
-        c->stats.kernels_launched += 2;
+        if(want_hash) direct_resolve_kernel<true><<<dim3(128, n), 256, 0, s>>>(dp);
+        else direct_resolve_kernel<false><<<dim3(128, n), 256, 0, s>>>(dp);
+        c->stats.kernels_launched++;
+        CU(cudaStreamWaitEvent(s, c->side_done, 0));
     }
     else
     {
@@ -273,6 +282,9 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
         c->ctas_per_sm = std::min(resident, 16);
     cudaError_t s1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t s2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+    if(s1 == cudaSuccess) s1 = cudaEventCreateWithFlags(&c->side_go, cudaEventDisableTiming);
+    if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
     for(int k = 0; k < 2 && s1 == cudaSuccess && s2 == cudaSuccess; k++)
     {
         s1 = cudaEventCreateWithFlags(&c->render_done[k], cudaEventDisableTiming);
@@ -464,6 +476,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         if(pixel_out || z_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(c->side_stream));
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
         for(int v = 0; v < nviews; v++)
@@ -597,6 +610,9 @@ void gelcu_destroy(gelcu_ctx* c)
     for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); }
     if(c->stream) cudaStreamDestroy(c->stream);
     if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if(c->side_stream) cudaStreamDestroy(c->side_stream);
+    if(c->side_go) cudaEventDestroy(c->side_go);
+    if(c->side_done) cudaEventDestroy(c->side_done);
     delete c;
 }
 
