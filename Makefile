@@ -15,7 +15,7 @@ CSTRICT   = -std=c99 -O2 -ffp-contract=off -Wall -Wextra -pedantic -fPIC
 
 all: gel_b200/libgelcu.so gel_b200/libgelhost.so gel_b200/host/gel oracle
 
-gel_b200/libgelcu.so: gel_b200/csrc/gelcu.cu gel_b200/csrc/gel_kernels.cuh gel_b200/csrc/gel_math.h include/gelcu.h
+gel_b200/libgelcu.so: $(wildcard gel_b200/csrc/*) include/gelcu.h
 	$(NVCC) $(NVFLAGS) -shared gel_b200/csrc/gelcu.cu -o $@
 
 gel_b200/libgelhost.so: gel_b200/host/gel_host.c gel_b200/host/gel_host.h

@@ -12,8 +12,9 @@ views are independent, each rank renders its own block, no collective on the ren
               step), mesh/texture/views resident in HBM, frames left in HBM; max over ranks
   e2e         same metric through the C ABI with HOST buffers: views from pinned host memory, every frame's
               pixels copied back to pinned host memory inside the timed region (wall clock, max over ranks)
-  roofline    dominant kernel (raster_kernel): algorithmic bytes per launch / its CUDA-event duration vs the
-              measured HBM peak (MEASURED_PEAKS.json); step_* = same with the whole step's kernels
+  roofline    dominant kernel (direct_raster_kernel<0> in the direct pipeline, raster_kernel in the tile pipeline):
+              algorithmic bytes per launch / its CUDA-event duration vs the measured HBM peak (MEASURED_PEAKS.json);
+              step_* = the same bytes over ALL the step's kernels (the figure the north-star target is about)
   cpu_baseline  the reference's CPU path on this box's host cores on a bounded sample (rank 0, N=1 only)
 `--impl reference` times the reference's own CPU implementation (oracle/_ref = unmodified main.c built headless,
 else the oracle port) frames-parallel on all host cores and prints the same line with "impl": "reference".
@@ -266,7 +267,7 @@ def measure_gpu(r, name, inputs, views, steps, warmup, rank_offset, flush):
         r.render(bases[s % len(bases)], pixels=False)
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
     t0 = time.time()
-    dev_ms, launches, stage = 0.0, 0, {"ms_transform": 0.0, "ms_bin": 0.0, "ms_raster": 0.0}
+    dev_ms, launches, stage = 0.0, 0, {"ms_transform": 0.0, "ms_bin": 0.0, "ms_raster": 0.0, "ms_dominant": 0.0}
     for s in range(steps):
         if flush is not None:
             flush.zero_(); torch.cuda.synchronize()
@@ -370,7 +371,9 @@ def main():
     worst_ms = max_over_ranks(dev_ms)
     total_views = sum_over_ranks(views) * args.steps
     fps = total_views / (worst_ms * 1e-3)
-    raster_ms = max_over_ranks(stage["ms_raster"])
+    raster_ms = max_over_ranks(stage["ms_dominant"])
+    pipeline = {1: "tile", 2: "direct"}.get(int(st.get("pipeline", 1)), "tile")
+    dominant = "direct_raster_kernel<0>" if pipeline == "direct" else "raster_kernel"
 
     # end to end through the C ABI with host buffers (pixels of every frame come back to pinned host memory)
     e2e_views = min(views, max(1, (2 << 30) // (4 * xres * yres)))
@@ -415,9 +418,9 @@ def main():
             "config": {"workload": f"{name}: {desc}", "triangles": ntri, "unique_vertices": int(st["unique_vertices"]), "resolution": f"{xres}x{yres}",
                        "views_per_step_per_gpu": views, "parallelism": f"views sharded over {world} GPU(s), mesh+texture replicated, no collective",
                        "l2": "flushed between steps (256 MiB write); a step also writes %.1f GB of frames" % (views * 8.0 * xres * yres / 1e9),
-                       "library_batches_per_step": int(st["batches"]), "bin_entries_per_view": st["bin_entries"] / max(1, st["views"]), "lit_pixels": lit},
+                       "library_batches_per_step": int(st["batches"]), "pipeline": pipeline, "bin_entries_per_view": st["bin_entries"] / max(1, st["views"]), "lit_pixels": lit},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "alg_bytes_per_frame": b_alg, "frames_per_launch": views_per_launch,
                          "launch_ms": raster_launch_ms, "step_achieved": step_achieved, "step_frac": step_achieved / peak},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]),

@@ -12,7 +12,8 @@
  *                             colour + z written once, coalesced
  *
  * The per-pixel arithmetic (numerators, exact cheap rejections, divisions, depth, shading) is shared with the tile
- * pipeline; only the staging differs.  No CTA-wide barrier is used in D1/D3: each warp owns its scratch.
+ * pipeline; only the staging differs.  D1/D3 run one warp per CTA (32 resident per SM): a warp that parks most of
+ * its triangles retires at once instead of idling beside slower warps of the same CTA.
  */
 #ifndef GEL_DIRECT_CUH
 #define GEL_DIRECT_CUH
@@ -21,7 +22,10 @@
 
 namespace gelk {
 
-constexpr int DIRECT_THREADS = 128;
+#ifndef GEL_DIRECT_THREADS
+#define GEL_DIRECT_THREADS 32
+#endif
+constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 constexpr int DIRECT_TRIS_PER_WARP = 256;          /* consecutive triangles a warp streams through */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
@@ -137,7 +141,7 @@ __device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned l
 }
 
 template<int PHASE>
-__global__ void __launch_bounds__(DIRECT_THREADS, 8)
+__global__ void __launch_bounds__(DIRECT_THREADS, 1024 / DIRECT_THREADS)
 direct_raster_kernel(DirectParams p)
 {
     __shared__ DirectScratch scratch[DIRECT_WARPS];

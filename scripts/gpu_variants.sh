@@ -1,8 +1,8 @@
 #!/bin/bash
-# compare tuning variants: bench (cfg3 + cfg2/5) per library, then the parity suite on the last one
+# compare tuning variants: bench per library (extra args after --), parity suite optional
 mkdir -p gpurun_out
 for lib in "$@"; do
   echo "== $lib"
-  GELCU_LIB=$lib timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_$lib.json 2> gpurun_out/bench_$lib.err; tail -2 gpurun_out/bench_$lib.err
+  GELCU_LIB=$lib timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-extra > gpurun_out/bench_$lib.json 2> gpurun_out/bench_$lib.err; tail -2 gpurun_out/bench_$lib.err
   python scripts/show_bench.py gpurun_out/bench_$lib.json
 done
