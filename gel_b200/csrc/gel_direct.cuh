@@ -410,23 +410,30 @@ direct_fill_kernel(DirectParams p)
     }
 }
 
-/* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): CTA g takes the region's
- * columns x0+g, x0+g+G, ...; one thread per pixel so the dependent loads of many pixels are in flight. */
+/* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): a CTA takes strips of 8
+ * adjacent columns (warp = column, lane = row), so the vertex / index / uv / texel lines of a triangle -- which
+ * spans a few columns and rows -- are reused out of L1 by neighbouring warps instead of being fetched by other SMs. */
 template<bool HASH>
 __global__ void __launch_bounds__(256)
 direct_resolve_kernel(DirectParams p)
 {
-    const int view = blockIdx.y;
+    const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int rx0, rx1, ry0, ry1;
     if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
     unsigned long long hp = 0, hz = 0;
-    for(int x = rx0 + blockIdx.x; x <= rx1; x += gridDim.x)
+    const int nstrips = (rx1 - rx0 + 8) / 8;
+    for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
+        const int x = rx0 + strip * 8 + warp;
+        if(x > rx1) continue;
         const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
-        for(int y = ry0 + threadIdx.x; y <= ry1; y += blockDim.x)
+        unsigned long long next_key = ry0 + lane <= ry1 ? p.keys[base + ry0 + lane] : CLEAR_KEY;
+        for(int y = ry0 + lane; y <= ry1; y += 32)
         {
+            const unsigned long long key = next_key;
+            if(y + 32 <= ry1) next_key = p.keys[base + y + 32];           /* one iteration ahead of its use */
             uint32_t colour; float z;
-            direct_shade(p, view, p.keys[base + y], x, y, colour, z);
+            direct_shade(p, view, key, x, y, colour, z);
             p.pixel[base + y] = colour;
             p.zbuf[base + y] = z;
             if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(colour, idx); hz += gel::salt_mix(__float_as_uint(z), idx); }
@@ -435,7 +442,7 @@ direct_resolve_kernel(DirectParams p)
     if(HASH)
     {
         for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
-        if((threadIdx.x & 31) == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
+        if(lane == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
     }
 }
 

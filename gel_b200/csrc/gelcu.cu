@@ -78,6 +78,10 @@ void free_work(gelcu_ctx* c)
     c->batch = 0; c->cap_e = 0; c->cap_d = 0;
 }
 
+#ifndef GEL_RESOLVE_CTAS
+#define GEL_RESOLVE_CTAS 128
+#endif
+constexpr int RESOLVE_CTAS = GEL_RESOLVE_CTAS;  /* CTAs per view in the direct pipeline's resolve pass (each walks strips of 8 columns) */
 constexpr int EV_PER_BATCH = 5;   /* start, after K1, after bin/clear, after the dominant raster kernel, end */
 
 int active_pipeline(const gelcu_ctx* c) { return c->pipeline_opt ? c->pipeline_opt : c->pipeline_auto; }
@@ -167,8 +171,16 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
         direct_clear_kernel<<<dim3(64, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
         CU(cudaEventRecord(ev[2], s));
-        /* everything outside the view's region is reset by pure stores: on the side stream, under the raster kernels */
-        CU(cudaEventRecord(c->side_go, s));
+        CU(cudaEventRecord(c->side_go, s));                              /* the region is known from here on */
+        if(c->ntri > 0)
+        {
+            direct_raster_kernel<0><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            c->stats.kernels_launched++;
+        }
+        CU(cudaEventRecord(ev[3], s));
+        /* everything outside the view's region is reset by pure stores on the side stream, submitted AFTER the near
+         * pass: D1 (one warp per CTA, 56 registers) leaves room for one fill CTA per SM, so this HBM traffic runs
+         * underneath the instruction-bound raster kernels */
         CU(cudaStreamWaitEvent(c->side_stream, c->side_go, 0));
         const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
         if(want_hash) direct_fill_kernel<true><<<fgrid, 256, 0, c->side_stream>>>(dp);
@@ -177,15 +189,12 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
         c->stats.kernels_launched++;
         if(c->ntri > 0)
         {
-            direct_raster_kernel<0><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
-            CU(cudaEventRecord(ev[3], s));
             direct_hiz_kernel<<<dim3(32, n), 256, 0, s>>>(dp);
             direct_raster_kernel<1><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
-            c->stats.kernels_launched += 3;
+            c->stats.kernels_launched += 2;
         }
-        else CU(cudaEventRecord(ev[3], s));
-        if(want_hash) direct_resolve_kernel<true><<<dim3(128, n), 256, 0, s>>>(dp);
-        else direct_resolve_kernel<false><<<dim3(128, n), 256, 0, s>>>(dp);
+        if(want_hash) direct_resolve_kernel<true><<<dim3(RESOLVE_CTAS, n), 256, 0, s>>>(dp);
+        else direct_resolve_kernel<false><<<dim3(RESOLVE_CTAS, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
         CU(cudaStreamWaitEvent(s, c->side_done, 0));
     }
