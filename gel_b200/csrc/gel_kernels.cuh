@@ -652,7 +652,7 @@ raster_kernel(RasterParams p)
             __syncwarp();
         };
 
-        /* large triangles: the whole CTA sweeps one triangle at a time; warp w takes columns w, w+W, .., lane = row;
+        /* large triangles: the whole CTA sweeps one triangle at a time in 4x8-pixel patches dealt to the warps;
          * survivors of the cheap tests are compacted so the divisions run in full warps */
         auto sweep_deferred = [&]()
         {
@@ -676,35 +676,43 @@ raster_kernel(RasterParams p)
                     const int src = li & 31;
                     const uint32_t bb = os.bbox[src];
                     const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
-                    const bool rowok = lane >= gy0 && lane <= gy1;
                     const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
                     const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src];
                     const float den_hi = q2.w * U_SLACK;
-                    const float v2y = gel::sub(gel::i2f(py0 + lane), q0.y);
-                    const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
-                    for(int xl = gx0 + ((warp - gx0) & (RASTER_WARPS - 1)); xl <= gx1; xl += RASTER_WARPS)
+                    /* the bbox is covered by patches of 4 columns x 8 rows (lane = 8*column + row): clipped bboxes are
+                     * rarely 32 rows tall, so this keeps far more lanes busy than one 32-row column per warp */
+                    const int pcols = (gx1 - gx0 + 4) >> 2, prows = (gy1 - gy0 + 8) >> 3;
+                    for(int pr = 0; pr < prows; pr++)
                     {
-                        const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
-                        const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
-                        const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
-                        const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
-                        const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                        const bool pass = rowok && may_be_inside(nv, nw, eps, den_hi);
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-                        if(pass)
+                        const int yl = gy0 + pr * 8 + (lane & 7);
+                        const bool rowok = yl <= gy1;
+                        const float v2y = gel::sub(gel::i2f(py0 + yl), q0.y);
+                        const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
+                        for(int pc = warp; pc < pcols; pc += RASTER_WARPS)
                         {
-                            const int slot = sq + __popc(m & lt_mask);
-                            ws.q_id[slot] = (uint32_t) li << 10 | (uint32_t) xl << 5 | (uint32_t) lane;
-                            ws.q_n[slot] = make_float2(nv, nw);
-                        }
-                        sq += __popc(m);
-                        if(sq >= 32)
-                        {
-                            /* divisions, inside test, depth, key for a full warp of survivors */
-                            __syncwarp();
-                            sq -= 32;
-                            resolve_swept(sm, ws, sq + lane);
-                            __syncwarp();
+                            const int xl = gx0 + pc * 4 + (lane >> 3);
+                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                            const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
+                            const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                            const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                            const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                            const bool pass = rowok && xl <= gx1 && may_be_inside(nv, nw, eps, den_hi);
+                            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                            if(pass)
+                            {
+                                const int slot = sq + __popc(m & lt_mask);
+                                ws.q_id[slot] = (uint32_t) li << 10 | (uint32_t) xl << 5 | (uint32_t) yl;
+                                ws.q_n[slot] = make_float2(nv, nw);
+                            }
+                            sq += __popc(m);
+                            if(sq >= 32)
+                            {
+                                /* divisions, inside test, depth, key for a full warp of survivors */
+                                __syncwarp();
+                                sq -= 32;
+                                resolve_swept(sm, ws, sq + lane);
+                                __syncwarp();
+                            }
                         }
                     }
                 }
