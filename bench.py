@@ -118,7 +118,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -130,7 +130,7 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def window(self, t0, t1):
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        rows = [r for (t, r) in self.rows if t0 - 0.02 <= t <= t1 + 0.05] or [r for (_, r) in self.rows[-3:]]
         sm, smax, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:

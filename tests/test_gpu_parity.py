@@ -215,6 +215,46 @@ def test_ties_degenerates_and_large_triangles():
         assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0), (0.25, 0.05)]))
 
 
+def test_hundreds_of_large_triangles_in_one_tile():
+    """More large (> 256 px in a tile) triangles than the CTA-wide sweep's list holds per round: the overflow goes
+    through the per-warp unit path instead; depth order and ties must still come out exactly."""
+    rng = np.random.default_rng(77)
+    n = 900
+    c = np.stack([rng.uniform(-0.02, 0.02, n), rng.uniform(0.48, 0.52, n), rng.uniform(-0.2, 0.2, n)], 1)
+    tv = np.empty((n, 3, 3), np.float32)
+    for k in range(3):
+        ang = rng.uniform(0, 2 * np.pi, n)
+        tv[:, k] = c + np.stack([0.12 * np.cos(ang), 0.12 * np.sin(ang), rng.uniform(-0.02, 0.02, n)], 1)
+    tv = tv.reshape(n, 9)
+    tn = np.tile(np.array([0, 0, 1], np.float32), (n, 3))
+    tt = rng.uniform(0, 1, (n, 9)).astype(np.float32)
+    tv = np.vstack([tv, tv[:50]]); tn = np.vstack([tn, tn[:50]]); tt = np.vstack([tt, rng.uniform(0, 1, (50, 9)).astype(np.float32)])
+    tex = small_tex(rng, 32, 32)
+    with make_renderer(640, 480, tv, tn, tt, tex) as r:
+        assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0), (0.1, 0.05)]))
+
+
+def test_thousands_of_far_triangles_in_one_tile():
+    """More parked (far) triangles in a single tile than its scratch holds (4096): the rest is rasterised in the
+    near phase.  A near occluder in front makes the hi-Z test reject most of the parked ones."""
+    rng = np.random.default_rng(78)
+    n = 7000
+    c = np.stack([rng.uniform(-0.03, 0.03, n), rng.uniform(0.52, 0.545, n), rng.uniform(-0.45, -0.35, n)], 1)   # far cluster, inside one 32x32 tile
+    tv = np.empty((n, 3, 3), np.float32)
+    for k in range(3):
+        ang = rng.uniform(0, 2 * np.pi, n)
+        tv[:, k] = c + np.stack([0.004 * np.cos(ang), 0.004 * np.sin(ang), rng.uniform(-0.001, 0.001, n)], 1)
+    tv = tv.reshape(n, 9)
+    occluder = np.array([[-0.2, 0.3, 0.4, 0.2, 0.3, 0.4, 0.0, 0.8, 0.4], [-0.2, 0.3, 0.4, 0.0, 0.8, 0.4, -0.3, 0.8, 0.4]], np.float32)
+    tv = np.vstack([occluder, tv, tv[:500]])
+    m = tv.shape[0]
+    tn = np.tile(np.array([0, 0, 1], np.float32), (m, 3))
+    tt = rng.uniform(0, 1, (m, 9)).astype(np.float32)
+    tex = small_tex(rng, 16, 16)
+    with make_renderer(800, 600, tv, tn, tt, tex) as r:
+        assert_views_match(r, tv, tn, tt, tex, gel_b200.view_bases([(0, 0), (0.05, 0.0)]))
+
+
 def test_texture_corners_and_shading_clamp_ends():
     """uv exactly 0 and 1 (texel (0, h-1) .. (w-1, 0)); normals facing away (intensity < 0 -> shading 0)."""
     tv = np.array([[-0.4, 0.1, 0, 0.4, 0.1, 0, 0.0, 0.9, 0], [-0.4, 0.1, -0.2, 0.4, 0.1, -0.2, 0.0, 0.9, -0.2]], np.float32)
