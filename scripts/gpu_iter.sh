@@ -6,4 +6,4 @@ for pl in 0 1 2; do
 done
 cp gpurun_out/pytest_gpu_p0.log gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
-if [ "$1" != "noprof" ]; then bash scripts/gpu_prof2.sh cfg3 8; fi
+if [ "$1" != "noprof" ]; then bash scripts/gpu_prof3.sh cfg3 8 direct_raster_kernel d1 8 2; fi
