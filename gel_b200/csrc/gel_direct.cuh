@@ -27,10 +27,16 @@ namespace gelk {
 #endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
-constexpr int DIRECT_TRIS_PER_WARP = 256;          /* consecutive triangles a warp streams through */
+#ifndef GEL_DIRECT_TPW
+#define GEL_DIRECT_TPW 1024
+#endif
+constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
 constexpr int DIRECT_UNIT_WINDOW = 512;
-constexpr int DIRECT_MAX_ROWS = 32;                /* taller (or > FRAG_MAX px) bboxes are swept by the whole warp */
+#ifndef GEL_DIRECT_MAX_ROWS
+#define GEL_DIRECT_MAX_ROWS 32
+#endif
+constexpr int DIRECT_MAX_ROWS = GEL_DIRECT_MAX_ROWS;                /* taller (or > FRAG_MAX px) bboxes are swept by the whole warp */
 constexpr int VSTAT = VIEW_STAT_WORDS;             /* per-view words: zlo, zhi, xmin, xmax, ymin, ymax, far count, - */
 
 struct DirectParams
