@@ -4,7 +4,9 @@
  * buffer in global memory with 64-bit atomic max (resolved in L2), using the same key as the tile pipeline:
  *     key = zkey(z) << 32 | (0xFFFFFFFF - triangle)         (main.c:356 semantics, see gel_kernels.cuh)
  *
- *   D0 direct_clear_kernel    key buffer := "no winner" inside the view's screen bbox (from K1), hi-Z := 0
+ *   D0 direct_clear_kernel    publishes the view's screen region (bbox from K1) and depth threshold, hi-Z := 0
+ *                             (the key buffer is "no winner" everywhere between batches: allocated that way, and the
+ *                             resolve pass puts every key it consumed back to that value)
  *   D1 direct_raster_kernel<0>  every triangle: near ones (max vertex z >= view midpoint) are rasterised, far ones parked
  *   D2 direct_hiz_kernel      per 8x8 pixel block: minimum depth key over its pixels
  *   D3 direct_raster_kernel<1>  parked triangles: dropped when provably behind every block they touch, else rasterised
@@ -100,12 +102,13 @@ direct_clear_kernel(DirectParams p)
         r[0] = any ? x0 : 0; r[1] = any ? x1 : -1; r[2] = any ? y0 : 0; r[3] = any ? y1 : -1;
         r[4] = __float_as_int(lo + 0.5f * (hi - lo));          /* near / far split of the view */
     }
-    if(!any) return;
-    for(int x = x0 + blockIdx.x; x <= x1; x += gridDim.x)
-    {
-        unsigned long long* col = p.keys + (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
-        for(int y = y0 + threadIdx.x; y <= y1; y += blockDim.x) col[y] = CLEAR_KEY;
-    }
+}
+
+/* whole key buffer := "no winner" (after allocation, or after a call that did not reach its resolve pass) */
+__global__ void __launch_bounds__(256)
+direct_keys_init_kernel(unsigned long long* keys, size_t n)
+{
+    for(size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) keys[i] = CLEAR_KEY;
 }
 
 /* D2 ------------------------------------------------------------------------------------------------------------ */
@@ -115,23 +118,25 @@ direct_hiz_kernel(DirectParams p)
     const int view = blockIdx.y;
     int x0, x1, y0, y1;
     if(!load_region(p, view, x0, x1, y0, y1)) return;
-    const int nbx = (x1 >> 3) - (x0 >> 3) + 1, nby = (y1 >> 3) - (y0 >> 3) + 1;
+    /* a warp takes 8 columns x 32 rows (4 blocks): lanes along y so every load is one contiguous 256-byte run */
+    const int nbx = (x1 >> 3) - (x0 >> 3) + 1, nby = (y1 >> 3) - (y0 >> 3) + 1, nby4 = (nby + 3) >> 2;
     const unsigned long long* keys = p.keys + (size_t) view * p.xres * p.yres;
-    for(int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbx * nby; b += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31, nwarps = gridDim.x * (blockDim.x >> 5);
+    for(int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); task < nbx * nby4; task += nwarps)
     {
-        const int bx = (x0 >> 3) + b / nby, by = (y0 >> 3) + b % nby;     /* neighbouring threads: neighbouring rows */
+        const int bx = (x0 >> 3) + task / nby4, by = (y0 >> 3) + (task % nby4) * 4 + (lane >> 3);
+        const int y = by * 8 + (lane & 7);
+        const bool live = y < p.yres && by <= (y1 >> 3);
         uint32_t lowest = 0xFFFFFFFFu;
-        for(int dx = 0; dx < 8; dx++)
+        if(live)
         {
-            const int x = bx * 8 + dx;
-            if(x >= p.xres) break;
-            for(int dy = 0; dy < 8; dy++)
-            {
-                const int y = by * 8 + dy;
-                if(y < p.yres) lowest = min(lowest, (uint32_t) (keys[(size_t) y + (size_t) x * p.yres] >> 32));
-            }
+            const unsigned long long* col = keys + (size_t) y + (size_t) bx * 8 * p.yres;
+#pragma unroll
+            for(int dx = 0; dx < 8; dx++)
+                if(bx * 8 + dx < p.xres) lowest = min(lowest, (uint32_t) (col[(size_t) dx * p.yres] >> 32));
         }
-        p.hiz[(size_t) view * p.hbx * p.hby + (size_t) bx * p.hby + by] = lowest;
+        for(int d = 1; d < 8; d <<= 1) lowest = min(lowest, __shfl_xor_sync(0xFFFFFFFFu, lowest, d));
+        if(live && (lane & 7) == 0) p.hiz[(size_t) view * p.hbx * p.hby + (size_t) bx * p.hby + by] = lowest;
     }
 }
 
@@ -440,6 +445,7 @@ direct_resolve_kernel(DirectParams p)
             if(y + 32 <= ry1) next_key = p.keys[base + y + 32];           /* one iteration ahead of its use */
             uint32_t colour; float z;
             direct_shade(p, view, key, x, y, colour, z);
+            p.keys[base + y] = CLEAR_KEY;                                 /* the buffer is all "no winner" again for the next batch */
             p.pixel[base + y] = colour;
             p.zbuf[base + y] = z;
             if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(colour, idx); hz += gel::salt_mix(__float_as_uint(z), idx); }

@@ -46,7 +46,7 @@ struct gelcu_ctx
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;   /* side: HBM-bound fill overlapping the raster kernels */
     cudaEvent_t side_go = nullptr, side_done = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
-    int ntri = 0, nuniq = 0; bool have_mesh = false;
+    int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr;
     /* texture */
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
@@ -109,6 +109,7 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
     if(pipe == 2)
     {
         CU(cudaMalloc(&c->d_keys, sizeof(unsigned long long) * B * frame));
+        c->keys_dirty = true;                                   /* filled with "no winner" before the first batch */
         CU(cudaMalloc(&c->d_hiz, sizeof(uint32_t) * (size_t) B * c->hbx * c->hby));
         CU(cudaMalloc(&c->d_parked, sizeof(uint4) * std::max<size_t>(1, (size_t) B * c->ntri)));
         CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP + DIRECT_WARPS + 1)));
@@ -459,6 +460,14 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         c->stats.kernels_launched = 0; c->stats.h2d_bytes = 0; c->stats.d2h_bytes = 0; c->stats.batches = nb; c->stats.views = nviews;
         CU(cudaMemcpyAsync(c->d_views, views, sizeof(gelcu_view) * nviews, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += sizeof(gelcu_view) * (size_t) nviews;
+        if(c->d_keys && c->keys_dirty)
+        {
+            /* the resolve pass leaves the key buffer all "no winner"; only a fresh allocation or a call that failed
+             * half way needs the whole buffer written */
+            direct_keys_init_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_keys, (size_t) c->batch * frame);
+            CU(cudaGetLastError());
+        }
+        c->keys_dirty = true;
 
         auto issue_copies = [&](int b) -> int {
             const int buf = b & 1, first = b * c->batch, n = std::min(c->batch, nviews - first);
@@ -486,6 +495,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->side_stream));
+        c->keys_dirty = false;
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
         for(int v = 0; v < nviews; v++)
