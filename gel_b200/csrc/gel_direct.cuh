@@ -34,7 +34,9 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #endif
 constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
-constexpr int DIRECT_UNIT_WINDOW = 512;
+constexpr int DIRECT_UNIT_WINDOW = 256;
+constexpr int DIRECT_CAND = 256;                 /* ring of hi-Z survivors waiting for a full batch (phase 1) */
+constexpr int DIRECT_TEST_UNROLL = 4;            /* parked records tested per lane per refill round */
 #ifndef GEL_DIRECT_MAX_ROWS
 #define GEL_DIRECT_MAX_ROWS 32
 #endif
@@ -60,6 +62,7 @@ struct DirectScratch               /* per warp */
 {
     float4 slab[4][32];
     uint32_t unit[DIRECT_UNIT_WINDOW];   /* lane << 13 | x */
+    uint32_t cand[DIRECT_CAND];          /* triangle ids */
     float2 q_n[QCAP];
     uint32_t q_id[QCAP];                 /* lane << 26 | x << 13 | y */
     uint32_t bx[32], by[32];             /* x0 | x1 << 16 ;  y0 | y1 << 13 | guard << 26 */
@@ -172,15 +175,18 @@ direct_raster_kernel(DirectParams p)
     int qn = 0, parked = 0;
     bool clipped = false;
 
-    for(int t0 = first; t0 < last; t0 += 32)
+    int tnext = first, chead = 0, ncand = 0;
+    for(;;)
     {
-        const int t = t0 + lane;
         bool have = false, park = false;
         uint32_t tri = 0, pbx = 0, pby = 0, bound = 0;
         float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-        if(t < last)
+        if(PHASE == 0)
         {
-            if(PHASE == 0)
+            if(tnext >= last) break;
+            const int t = tnext + lane;
+            tnext += 32;
+            if(t < last)
             {
                 tri = (uint32_t) t;
                 a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
@@ -196,24 +202,53 @@ direct_raster_kernel(DirectParams p)
                     bound = depth_bound_key(zmax);
                 }
             }
-            else
+        }
+        else
+        {
+            /* the parked records are tested against the hi-Z map several per lane (independent loads in flight);
+             * the few survivors wait in a ring until a full batch of 32 can be rasterised */
+            while(ncand < 32 && tnext < last)
             {
-                const uint4 rec = far[t];
-                const int gx0 = (rec.y & 0xFFFF) >> 3, gx1 = (rec.y >> 16) >> 3, gy0 = (rec.z & 0xFFFF) >> 3, gy1 = (rec.z >> 16) >> 3;
-                bool survive = true;
-                if(gx1 - gx0 <= 1 && gy1 - gy0 <= 1)
+                uint4 rec[DIRECT_TEST_UNROLL];
+                bool survive[DIRECT_TEST_UNROLL];
+#pragma unroll
+                for(int k = 0; k < DIRECT_TEST_UNROLL; k++)
                 {
-                    const uint32_t lowest = min(min(__ldg(hiz + gx0 * p.hby + gy0), __ldg(hiz + gx0 * p.hby + gy1)),
-                                                min(__ldg(hiz + gx1 * p.hby + gy0), __ldg(hiz + gx1 * p.hby + gy1)));
-                    survive = !(rec.w < lowest);
+                    const int t = tnext + k * 32 + lane;
+                    rec[k] = t < last ? far[t] : make_uint4(0u, 0u, 0u, 0u);
+                    survive[k] = t < last;
                 }
-                if(survive)
+#pragma unroll
+                for(int k = 0; k < DIRECT_TEST_UNROLL; k++)
                 {
-                    tri = rec.x;
-                    a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
-                    have = true;
+                    const int gx0 = (rec[k].y & 0xFFFF) >> 3, gx1 = (rec[k].y >> 16) >> 3, gy0 = (rec[k].z & 0xFFFF) >> 3, gy1 = (rec[k].z >> 16) >> 3;
+                    if(survive[k] && gx1 - gx0 <= 1 && gy1 - gy0 <= 1)
+                    {
+                        const uint32_t lowest = min(min(__ldg(hiz + gx0 * p.hby + gy0), __ldg(hiz + gx0 * p.hby + gy1)),
+                                                    min(__ldg(hiz + gx1 * p.hby + gy0), __ldg(hiz + gx1 * p.hby + gy1)));
+                        survive[k] = !(rec[k].w < lowest);
+                    }
                 }
+#pragma unroll
+                for(int k = 0; k < DIRECT_TEST_UNROLL; k++)
+                {
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, survive[k]);
+                    if(survive[k]) ws.cand[(chead + ncand + __popc(m & lt_mask)) & (DIRECT_CAND - 1)] = rec[k].x;
+                    ncand += __popc(m);
+                }
+                tnext += 32 * DIRECT_TEST_UNROLL;
             }
+            if(ncand == 0) break;
+            __syncwarp();
+            const int take = min(ncand, 32);
+            if(lane < take)
+            {
+                tri = ws.cand[(chead + lane) & (DIRECT_CAND - 1)];
+                a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                have = true;
+            }
+            chead += take; ncand -= take;
+            __syncwarp();
         }
         if(PHASE == 0)
         {
