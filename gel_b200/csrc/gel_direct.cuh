@@ -29,6 +29,10 @@ namespace gelk {
 #endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
+constexpr int TREC_QUADS = 4;                    /* 64-byte static record per triangle for the resolve pass */
+#ifndef GEL_RESOLVE_MINB
+#define GEL_RESOLVE_MINB 8        /* resident CTAs per SM the resolve pass is compiled for (32 registers): it is latency bound */
+#endif
 #ifndef GEL_DIRECT_TPW
 #define GEL_DIRECT_TPW 1024
 #endif
@@ -45,7 +49,7 @@ constexpr int VSTAT = VIEW_STAT_WORDS;             /* per-view words: zlo, zhi, 
 
 struct DirectParams
 {
-    const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
+    const float4* xf; const uint32_t *i0, *i1, *i2; const uint4* trec;   /* trec: TREC_QUADS x 16 bytes per triangle: {i0,i1,i2,-} {u0,v0,u1,v1} {u2,v2,-,-} */
     const uint32_t* tex; int tw, th;
     unsigned long long* keys;      /* [view][xres*yres]  index y + x*yres                                   */
     uint32_t* hiz;                 /* [view][hbx*hby]    min depth key per 8x8 block, index bx*hby + by     */
@@ -396,9 +400,11 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float4* xf = p.xf + (size_t) view * p.nuniq;
     const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
     z = gel::zkey_inv((uint32_t) (key >> 32));
-    const float4 a = __ldg(xf + __ldg(p.i0 + tri));
-    const float4 b = __ldg(xf + __ldg(p.i1 + tri));
-    const float4 c = __ldg(xf + __ldg(p.i2 + tri));
+    const uint4* rec = p.trec + (size_t) TREC_QUADS * tri;
+    const uint4 ri = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+    const float4 a = __ldg(xf + ri.x);
+    const float4 b = __ldg(xf + ri.y);
+    const float4 c = __ldg(xf + ri.z);
     /* tbarycenter at this pixel (main.c:316-332), same operations and operands as the visibility pass */
     const float v0x = gel::sub(b.x, a.x), v0y = gel::sub(b.y, a.y), v0z = gel::sub(b.z, a.z);
     const float v1x = gel::sub(c.x, a.x), v1y = gel::sub(c.y, a.y), v1z = gel::sub(c.z, a.z);
@@ -410,8 +416,7 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float v = gel::dvd(gel::sub(gel::mul(d11, d20), gel::mul(d01, d21)), den);
     const float w = gel::dvd(gel::sub(gel::mul(d00, d21), gel::mul(d01, d20)), den);
     const float u = gel::sub(gel::sub(1.0f, v), w);
-    const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
-    const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
+    const float uv[6] = { __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w), __uint_as_float(r2.x), __uint_as_float(r2.y) };
     int xx, yy, shading;
     gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
     if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
@@ -460,7 +465,7 @@ direct_fill_kernel(DirectParams p)
  * adjacent columns (warp = column, lane = row), so the vertex / index / uv / texel lines of a triangle -- which
  * spans a few columns and rows -- are reused out of L1 by neighbouring warps instead of being fetched by other SMs. */
 template<bool HASH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GEL_RESOLVE_MINB)
 direct_resolve_kernel(DirectParams p)
 {
     const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

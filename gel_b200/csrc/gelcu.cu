@@ -47,7 +47,7 @@ struct gelcu_ctx
     cudaEvent_t side_go = nullptr, side_done = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
-    float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr;
+    float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr;
     /* texture */
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
@@ -165,7 +165,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
     CU(cudaEventRecord(ev[1], s));
     if(pipe == 2)
     {
-        DirectParams dp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_tex, c->tw, c->th, c->d_keys, c->d_hiz, c->d_parked, c->d_far_count, c->d_region, c->d_vstat,
+        DirectParams dp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_trec, c->d_tex, c->tw, c->th, c->d_keys, c->d_hiz, c->d_parked, c->d_far_count, c->d_region, c->d_vstat,
                             c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->ntri, c->nuniq, c->xres, c->yres, c->hbx, c->hby, n };
         const int tris_per_cta = DIRECT_WARPS * DIRECT_TRIS_PER_WARP;
         const dim3 rgrid((c->ntri + tris_per_cta - 1) / tris_per_cta, n);
@@ -379,13 +379,26 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
     std::vector<float2> uv(ncorner);
     for(size_t cidx = 0; cidx < ncorner; cidx++) uv[cidx] = make_float2(tt[3 * cidx], tt[3 * cidx + 1]);   /* tt.z is never read, main.c:360-361 */
 
+    /* the direct pipeline's resolve pass gathers per winning pixel: one 64-byte record per triangle (vertex indices +
+     * texture coordinates) costs three 16-byte loads in one cache line instead of six loads in four arrays */
+    std::vector<uint4> trec((size_t) TREC_QUADS * ntri, make_uint4(0u, 0u, 0u, 0u));
+    for(int t = 0; t < ntri; t++)
+    {
+        uint32_t w[8];
+        memcpy(w, &uv[3 * (size_t) t], 24);
+        trec[(size_t) TREC_QUADS * t] = make_uint4(idx[0][t], idx[1][t], idx[2][t], 0u);
+        trec[(size_t) TREC_QUADS * t + 1] = make_uint4(w[0], w[1], w[2], w[3]);
+        trec[(size_t) TREC_QUADS * t + 2] = make_uint4(w[4], w[5], 0u, 0u);
+    }
+
     free_work(c);
-    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv);
+    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
     c->ntri = ntri; c->nuniq = (int) vpos.size(); c->have_mesh = true;
     const size_t nu = std::max<size_t>(1, vpos.size()), nt = std::max<size_t>(1, (size_t) ntri);
     CU(cudaMalloc(&c->d_vpos, sizeof(float4) * nu)); CU(cudaMalloc(&c->d_vnrm, sizeof(float4) * nu));
     CU(cudaMalloc(&c->d_i0, 4 * nt)); CU(cudaMalloc(&c->d_i1, 4 * nt)); CU(cudaMalloc(&c->d_i2, 4 * nt));
     CU(cudaMalloc(&c->d_uv, sizeof(float2) * 3 * nt));
+    CU(cudaMalloc(&c->d_trec, sizeof(uint4) * TREC_QUADS * nt));
     if(ntri > 0)
     {
         CU(cudaMemcpy(c->d_vpos, vpos.data(), sizeof(float4) * vpos.size(), cudaMemcpyHostToDevice));
@@ -394,6 +407,7 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         CU(cudaMemcpy(c->d_i1, idx[1].data(), 4 * (size_t) ntri, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_i2, idx[2].data(), 4 * (size_t) ntri, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_uv, uv.data(), sizeof(float2) * uv.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_trec, trec.data(), sizeof(uint4) * trec.size(), cudaMemcpyHostToDevice));
     }
     return GELCU_OK;
 }
@@ -620,7 +634,7 @@ void gelcu_destroy(gelcu_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_work(c);
-    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv);
+    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
     dfree(c->d_tex); dfree(c->d_views);
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
