@@ -29,13 +29,17 @@ namespace gelk {
 #endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
-constexpr int TREC_QUADS = 4;                    /* 64-byte static record per triangle for the resolve pass */
+#ifndef GEL_RESOLVE_WCOLS
+#define GEL_RESOLVE_WCOLS 4        /* columns of a resolve warp's pixel footprint (x 32/WCOLS rows); 1, 2, 4 or 8 */
+#endif
 #ifndef GEL_RESOLVE_MINB
 #define GEL_RESOLVE_MINB 8        /* resident CTAs per SM the resolve pass is compiled for (32 registers): it is latency bound */
 #endif
 #ifndef GEL_DIRECT_TPW
 #define GEL_DIRECT_TPW 1024
 #endif
+constexpr int RESOLVE_WCOLS = GEL_RESOLVE_WCOLS;
+constexpr int TREC_QUADS = 4;                    /* 64-byte static record per triangle for the resolve pass */
 constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
 constexpr int DIRECT_UNIT_WINDOW = 256;
@@ -462,27 +466,31 @@ direct_fill_kernel(DirectParams p)
 }
 
 /* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): a CTA takes strips of 8
- * adjacent columns (warp = column, lane = row), so the vertex / index / uv / texel lines of a triangle -- which
- * spans a few columns and rows -- are reused out of L1 by neighbouring warps instead of being fetched by other SMs. */
+ * adjacent columns, 32 rows at a time; a warp covers RESOLVE_WCOLS columns x (32 / RESOLVE_WCOLS) rows of them.  The
+ * compact footprint is what keeps the gathers cheap: a warp's 32 pixels then touch few distinct triangles, vertices
+ * and -- above all -- texture rows (a 1 x 32 column touched ~30 texture lines per texel load, the L1 data pipe was
+ * the kernel's limit), and neighbouring warps reuse the same lines out of L1. */
 template<bool HASH>
 __global__ void __launch_bounds__(256, GEL_RESOLVE_MINB)
 direct_resolve_kernel(DirectParams p)
 {
+    constexpr int WROWS = 32 / RESOLVE_WCOLS, WARPS_X = 8 / RESOLVE_WCOLS, WARPS_Y = 8 / WARPS_X, CTA_ROWS = WROWS * WARPS_Y;
     const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = (warp % WARPS_X) * RESOLVE_WCOLS + lane / WROWS, py = (warp / WARPS_X) * WROWS + lane % WROWS;
     int rx0, rx1, ry0, ry1;
     if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
     unsigned long long hp = 0, hz = 0;
     const int nstrips = (rx1 - rx0 + 8) / 8;
     for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
-        const int x = rx0 + strip * 8 + warp;
+        const int x = rx0 + strip * 8 + px;
         if(x > rx1) continue;
         const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
-        unsigned long long next_key = ry0 + lane <= ry1 ? p.keys[base + ry0 + lane] : CLEAR_KEY;
-        for(int y = ry0 + lane; y <= ry1; y += 32)
+        unsigned long long next_key = ry0 + py <= ry1 ? p.keys[base + ry0 + py] : CLEAR_KEY;
+        for(int y = ry0 + py; y <= ry1; y += CTA_ROWS)
         {
             const unsigned long long key = next_key;
-            if(y + 32 <= ry1) next_key = p.keys[base + y + 32];           /* one iteration ahead of its use */
+            if(y + CTA_ROWS <= ry1) next_key = p.keys[base + y + CTA_ROWS];   /* one iteration ahead of its use */
             uint32_t colour; float z;
             direct_shade(p, view, key, x, y, colour, z);
             p.keys[base + y] = CLEAR_KEY;                                 /* the buffer is all "no winner" again for the next batch */
