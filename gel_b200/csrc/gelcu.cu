@@ -480,6 +480,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
              * half way needs the whole buffer written */
             direct_keys_init_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_keys, (size_t) c->batch * frame);
             CU(cudaGetLastError());
+            c->stats.kernels_launched++;
         }
         c->keys_dirty = true;
 
