@@ -25,7 +25,7 @@ GELCU_E_INVALID, GELCU_E_CUDA, GELCU_E_NOMEM, GELCU_E_NOGPU = -1, -2, -3, -4
 
 # every symbol include/gelcu.h declares (tests check the library exports exactly these)
 GELCU_SYMBOLS = [
-    "gelcu_device_count", "gelcu_create", "gelcu_set_mesh", "gelcu_set_texture", "gelcu_render",
+    "gelcu_device_count", "gelcu_create", "gelcu_set_mesh", "gelcu_set_texture", "gelcu_render", "gelcu_render_rgb8",
     "gelcu_read_frame", "gelcu_set_option", "gelcu_get_stats", "gelcu_debug_transform", "gelcu_debug_bins",
     "gelcu_tile_grid", "gelcu_host_alloc", "gelcu_host_free", "gelcu_destroy", "gelcu_last_error",
 ]
@@ -69,6 +69,7 @@ def cu() -> ctypes.CDLL:
         L.gelcu_set_mesh.argtypes = [c_void_p, _fp, _fp, _fp, c_int]
         L.gelcu_set_texture.argtypes = [c_void_p, _u32p, c_int, c_int]
         L.gelcu_render.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, _fp]
+        L.gelcu_render_rgb8.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, _fp]
         L.gelcu_read_frame.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
         L.gelcu_set_option.argtypes = [c_void_p, c_char_p, c_int]
         L.gelcu_get_stats.argtypes = [c_void_p, POINTER(Stats)]
@@ -228,6 +229,20 @@ class Renderer:
                                       h.ctypes.data_as(c_void_p) if h is not None else None, byref(ms)))
         self.last_rc = rc
         return {"pixel": pixel_out, "z": z_out, "hash": h, "device_ms": float(ms.value), "rc": rc}
+
+    def render_rgb8(self, bases, *, hashes=False, rgb_out=None):
+        """Frame sink: upright 24-bit frames, (n, yres, xres, 3) uint8 (the body of a binary PPM each).  Returns
+        dict(rgb, hash, device_ms, rc)."""
+        b = np.ascontiguousarray(bases, dtype=np.float32).reshape(-1, 12)
+        n = b.shape[0]
+        if rgb_out is None:
+            rgb_out = np.empty((n, self.yres, self.xres, 3), dtype=np.uint8)
+        h = np.zeros((n, 2), dtype=np.uint64) if hashes else None
+        ms = c_float(0.0)
+        rc = _check(cu().gelcu_render_rgb8(self._ctx, b.ctypes.data_as(c_void_p), n, rgb_out.ctypes.data_as(c_void_p),
+                                           h.ctypes.data_as(c_void_p) if h is not None else None, byref(ms)))
+        self.last_rc = rc
+        return {"rgb": rgb_out, "hash": h, "device_ms": float(ms.value), "rc": rc}
 
     def read_frame(self, slot: int):
         frame = self.xres * self.yres

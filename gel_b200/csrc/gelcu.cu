@@ -10,6 +10,7 @@
  * Frames are double-buffered in HBM so the device->host copy of batch b overlaps the kernels of batch b+1.
  */
 #include "gel_direct.cuh"
+#include "gel_sink.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -59,6 +60,7 @@ struct gelcu_ctx
     double mean_tri_px = 0.0;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
+    uint8_t* d_rgb[2] = { nullptr, nullptr };   /* frame sink: upright 24-bit frames, allocated on first use */
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; int hcap = 0;
     uint32_t* h_vinit = nullptr;   /* pinned initial per-view statistics (VIEW_STAT_WORDS each) x MAX_BATCH */
@@ -74,7 +76,7 @@ void free_work(gelcu_ctx* c)
 {
     dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
-    dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]);
+    dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]); dfree(c->d_rgb[0]); dfree(c->d_rgb[1]);
     c->batch = 0; c->cap_e = 0; c->cap_d = 0;
 }
 
@@ -142,7 +144,7 @@ int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 }
 
 /* Enqueues the kernels for `n` views starting at d_views + first into frame buffer `buf`. */
-int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaEvent_t* ev)
+int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool want_rgb, cudaEvent_t* ev)
 {
     cudaStream_t s = c->stream;
     const int pipe = c->work_pipeline;
@@ -219,6 +221,13 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, cudaE
         CU(cudaEventRecord(ev[3], s));
     }
     CU(cudaEventRecord(ev[4], s));
+    if(want_rgb)
+    {
+        /* frame sink: un-rotated 24-bit copy for the device -> host transfer; after the path's last
+         * event, so the render figures (ms_total, device_ms) mean the same with and without it */
+        sink_rgb8_kernel<<<dim3((c->xres + SINK_TX - 1) / SINK_TX, (c->yres + SINK_TY - 1) / SINK_TY, n), SINK_THREADS, 0, s>>>(c->d_pixel[buf], c->d_rgb[buf], c->xres, c->yres);
+        c->stats.kernels_launched++;
+    }
     CU(cudaGetLastError());
     return GELCU_OK;
 }
@@ -443,8 +452,10 @@ int gelcu_get_stats(gelcu_ctx* c, gelcu_stats* out)
     return GELCU_OK;
 }
 
-int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
-                 uint32_t* pixel_out, float* z_out, uint64_t* hash_out, float* device_ms)
+namespace {
+
+int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
+                uint32_t* pixel_out, float* z_out, uint8_t* rgb_out, uint64_t* hash_out, float* device_ms)
 {
     int rc = check_ready(c);
     if(rc) return rc;
@@ -469,6 +480,8 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
     {
         const int B = std::min(nviews, std::max(c->batch, default_batch(c, cap_e, cap_d)));
         rc = ensure_work(c, B, cap_e, cap_d); if(rc) return rc;
+        if(rgb_out && !c->d_rgb[0])
+            for(int k = 0; k < 2; k++) CU(cudaMalloc(&c->d_rgb[k], 3 * frame * (size_t) c->batch));
         const int nb = (nviews + c->batch - 1) / c->batch;
         rc = ensure_events(c, nb); if(rc) return rc;
         c->stats.kernels_launched = 0; c->stats.h2d_bytes = 0; c->stats.d2h_bytes = 0; c->stats.batches = nb; c->stats.views = nviews;
@@ -489,6 +502,7 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
             CU(cudaStreamWaitEvent(c->copy_stream, c->render_done[buf], 0));
             if(pixel_out) { CU(cudaMemcpyAsync(pixel_out + frame * first, c->d_pixel[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
             if(z_out) { CU(cudaMemcpyAsync(z_out + frame * first, c->d_z[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
+            if(rgb_out) { CU(cudaMemcpyAsync(rgb_out + 3 * frame * first, c->d_rgb[buf], 3 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 3 * frame * n; }
             CU(cudaEventRecord(c->copy_done[buf], c->copy_stream));
             return GELCU_OK;
         };
@@ -497,16 +511,16 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         {
             const int buf = b & 1, first = b * c->batch, n = std::min(c->batch, nviews - first);
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
-            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
+            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, rgb_out != nullptr, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
             /* small per-batch results ride the render stream (the next batch overwrites their device copies) */
             CU(cudaMemcpyAsync(c->h_cursors + 4 * first, c->d_cursors, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaMemcpyAsync(c->h_flags + first, c->d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
             if(hash_out) { CU(cudaMemcpyAsync(hash_out + 2 * (size_t) first, c->d_hash, 16 * (size_t) n, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2h_bytes += 16 * (size_t) n; }
             CU(cudaEventRecord(c->render_done[buf], c->stream));
-            if(b >= 1 && (pixel_out || z_out)) { rc = issue_copies(b - 1); if(rc) return rc; }
+            if(b >= 1 && (pixel_out || z_out || rgb_out)) { rc = issue_copies(b - 1); if(rc) return rc; }
             c->last_batch_views = n; c->last_buf = buf;
         }
-        if(pixel_out || z_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
+        if(pixel_out || z_out || rgb_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->side_stream));
@@ -551,6 +565,20 @@ int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
         return GELCU_OK;
     }
     return fail(GELCU_E_NOMEM, "bin list capacity did not converge");
+}
+
+} /* namespace */
+
+int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
+                 uint32_t* pixel_out, float* z_out, uint64_t* hash_out, float* device_ms)
+{
+    return render_impl(c, views, nviews, pixel_out, z_out, nullptr, hash_out, device_ms);
+}
+
+int gelcu_render_rgb8(gelcu_ctx* c, const gelcu_view* views, int nviews, uint8_t* rgb_out, uint64_t* hash_out, float* device_ms)
+{
+    if(!rgb_out && nviews > 0) return fail(GELCU_E_INVALID, "null rgb_out");
+    return render_impl(c, views, nviews, nullptr, nullptr, rgb_out, hash_out, device_ms);
 }
 
 int gelcu_read_frame(gelcu_ctx* c, int slot, uint32_t* pixel_out, float* z_out)

@@ -9,7 +9,9 @@
  *   iinit / ipump (mouse)                     scripted input: --mouse DX,DY per frame, or --sweep N
  *   slock .. reset .. tdraw loop .. sunlock   gelcu_render(views...)
  *   schurn / spresent                         per-frame JSON line (FNV-1a-64, non-zero pixels), optional
- *                                             raw dump (--dump) or upright PPM (--ppm)
+ *                                             raw dump (--dump) or upright PPM (--ppm); with --sink rgb8 the
+ *                                             un-rotation + 24-bit pack happen on the device
+ *                                             (gelcu_render_rgb8) and --ppm writes the buffer as it arrives
  *   60 fps cap                                none (headless)
  *
  * Exit status and messages follow the reference: wrong argument count prints the usage line and returns
@@ -29,9 +31,9 @@
 
 typedef struct
 {
-    int device, first, count, xres, yres, batch, readback;
+    int device, first, count, xres, yres, batch, readback, sink;
     const GelMesh* mesh; const GelTexture* tex; const gelcu_view* views;
-    uint32_t* pixels;        /* count frames (readback) */
+    uint32_t* pixels;        /* count frames (readback); with sink: count upright 24-bit frames */
     uint64_t* hashes;        /* 2 per view */
     float device_ms; double wall_s; int rc; char err[512];
     gelcu_stats stats;
@@ -56,7 +58,8 @@ static void* shard_main(void* arg)
     if(s->rc == 0)
     {
         const double t0 = now_s();
-        s->rc = gelcu_render(ctx, s->views + s->first, s->count, s->readback ? s->pixels : NULL, NULL, s->hashes, &s->device_ms);
+        if(s->sink && s->readback) s->rc = gelcu_render_rgb8(ctx, s->views + s->first, s->count, (uint8_t*) s->pixels, s->hashes, &s->device_ms);
+        else s->rc = gelcu_render(ctx, s->views + s->first, s->count, s->readback ? s->pixels : NULL, NULL, s->hashes, &s->device_ms);
         s->wall_s = now_s() - t0;
         gelcu_get_stats(ctx, &s->stats);
     }
@@ -68,7 +71,7 @@ static void* shard_main(void* arg)
 int main(int argc, char* argv[])
 {
     const char* positional[2] = { NULL, NULL };
-    int npos = 0, xres = 800, yres = 600, frames = 1, dx = 0, dy = 0, sweep = 0, gpus = 1, batch = 0, readback = 1;
+    int npos = 0, xres = 800, yres = 600, frames = 1, dx = 0, dy = 0, sweep = 0, gpus = 1, batch = 0, readback = 1, sink = 0;
     const char* dump_path = NULL; const char* ppm_prefix = NULL;
     for(int i = 1; i < argc; i++)
     {
@@ -81,6 +84,7 @@ int main(int argc, char* argv[])
         else if(!strcmp(argv[i], "--dump") && i + 1 < argc) dump_path = argv[++i];
         else if(!strcmp(argv[i], "--ppm") && i + 1 < argc) ppm_prefix = argv[++i];
         else if(!strcmp(argv[i], "--no-readback")) readback = 0;
+        else if(!strcmp(argv[i], "--sink") && i + 1 < argc) { if(!strcmp(argv[++i], "rgb8")) sink = 1; else npos = 99; }
         else if(argv[i][0] == '-' && argv[i][1] == '-') npos = 99;
         else if(npos < 2) positional[npos++] = argv[i];
         else npos = 99;
@@ -89,7 +93,7 @@ int main(int argc, char* argv[])
     {
         puts("args: path/to/obj path/to/bmp");
         puts("      [--res WxH] [--frames N] [--mouse DX,DY] [--sweep N] [--gpus G] [--batch B]");
-        puts("      [--dump frames.raw] [--ppm prefix] [--no-readback]");
+        puts("      [--dump frames.raw] [--ppm prefix] [--no-readback] [--sink rgb8]");
         return 1;
     }
     GelMesh mesh; GelTexture tex;
@@ -116,9 +120,10 @@ int main(int argc, char* argv[])
     if(gpus > nviews) gpus = nviews;
 
     const size_t frame = (size_t) xres * yres;
+    const size_t frame_bytes = frame * (sink ? 3 : 4);                   /* sink: upright 24-bit frames come back */
     FILE* dump = dump_path ? fopen(dump_path, "wb") : NULL;
     /* frames come back in chunks so that long sweeps do not need nviews frames of host memory */
-    const int chunk = readback ? (int) (((size_t) 1 << 30) / (frame * 4) > 0 ? ((size_t) 1 << 30) / (frame * 4) : 1) : nviews;
+    const int chunk = readback ? (int) (((size_t) 1 << 30) / frame_bytes > 0 ? ((size_t) 1 << 30) / frame_bytes : 1) : nviews;
     uint64_t* hashes = (uint64_t*) calloc((size_t) 2 * nviews, sizeof(uint64_t));
     double dev_ms_max_sum = 0.0, wall_sum = 0.0;
     uint64_t launches = 0;
@@ -129,12 +134,12 @@ int main(int argc, char* argv[])
         Shard shards[64]; pthread_t th[64];
         const int g_used = gpus > 64 ? 64 : gpus;
         uint32_t* pixels = NULL;
-        if(readback && gelcu_host_alloc((void**) &pixels, frame * 4 * (size_t) n) != 0) { printf("host alloc failed: %s\n", gelcu_last_error()); exit(1); }
+        if(readback && gelcu_host_alloc((void**) &pixels, frame_bytes * (size_t) n) != 0) { printf("host alloc failed: %s\n", gelcu_last_error()); exit(1); }
         for(int g = 0; g < g_used; g++)
         {
             const int lo = (int) ((long long) n * g / g_used), hi = (int) ((long long) n * (g + 1) / g_used);
-            Shard s = { g, base + lo, hi - lo, xres, yres, batch, readback, &mesh, &tex, views,
-                        readback ? pixels + frame * lo : NULL, hashes + 2 * (size_t) (base + lo), 0.0f, 0.0, 0, "", { 0 } };
+            Shard s = { g, base + lo, hi - lo, xres, yres, batch, readback, sink, &mesh, &tex, views,
+                        readback ? (uint32_t*) ((uint8_t*) pixels + frame_bytes * lo) : NULL, hashes + 2 * (size_t) (base + lo), 0.0f, 0.0, 0, "", { 0 } };
             shards[g] = s;
             pthread_create(&th[g], NULL, shard_main, &shards[g]);
         }
@@ -151,7 +156,25 @@ int main(int argc, char* argv[])
         dev_ms_max_sum += ms_max; wall_sum += wall_max;
         for(int k = 0; k < n; k++)
         {
-            if(readback)
+            if(readback && sink)
+            {
+                /* the frame is already upright RGB: checksum over its bytes, PPM = header + the buffer */
+                const uint8_t* rgb = (const uint8_t*) pixels + frame_bytes * k;
+                uint64_t h = 0xcbf29ce484222325ull; size_t nonzero = 0;
+                for(size_t i = 0; i < frame_bytes; i++) h = (h ^ rgb[i]) * 0x100000001b3ull;
+                for(size_t i = 0; i < frame; i++) nonzero += (rgb[3 * i] | rgb[3 * i + 1] | rgb[3 * i + 2]) != 0;
+                printf("{\"frame\": %d, \"rgb_fnv\": \"%016llx\", \"nonzero\": %zu, \"checksum\": \"%016llx\"}\n", base + k,
+                       (unsigned long long) h, nonzero, (unsigned long long) hashes[2 * (size_t) (base + k)]);
+                if(dump) fwrite(rgb, 1, frame_bytes, dump);
+                if(ppm_prefix)
+                {
+                    char path[1024];
+                    snprintf(path, sizeof path, "%s%04d.ppm", ppm_prefix, base + k);
+                    FILE* f = fopen(path, "wb");
+                    if(f) { fprintf(f, "P6\n%d %d\n255\n", xres, yres); fwrite(rgb, 1, frame_bytes, f); fclose(f); }
+                }
+            }
+            else if(readback)
             {
                 const uint32_t* px = pixels + frame * k;
                 size_t nonzero = 0;

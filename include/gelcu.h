@@ -93,6 +93,17 @@ int gelcu_set_texture(gelcu_ctx* ctx, const uint32_t* xrgb, int w, int h);
 int gelcu_render(gelcu_ctx* ctx, const gelcu_view* views, int nviews,
                  uint32_t* pixel_out, float* z_out, uint64_t* hash_out, float* device_ms);
 
+/* Frame sink: the same render, but each frame leaves the device in presentation form --
+ * un-rotated the way schurn presents it (SDL_RenderCopyEx by -90 degrees, main.c:424-432) and packed to 24 bits:
+ *   rgb_out    host, nviews * yres rows * xres pixels * 3 bytes, top row first:
+ *              rgb_out[k][(wy*xres + wx)*3 + {0,1,2}] = {R,G,B} of view k's pixel[(yres-1-wy) + wx*yres]
+ *              (the body of a binary PPM "P6 xres yres 255").  The device -> host copy carries 3 bytes per pixel
+ *              instead of 4 and the host does not touch the pixels again.
+ *   hash_out, device_ms  as in gelcu_render (checksums are of the sideways XRGB / z frames; device_ms excludes
+ *              the sink kernel, like it excludes copies). */
+int gelcu_render_rgb8(gelcu_ctx* ctx, const gelcu_view* views, int nviews,
+                      uint8_t* rgb_out, uint64_t* hash_out, float* device_ms);
+
 /* Copies frame `slot` (0-based within the LAST batch of the previous gelcu_render) to the host. */
 int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out);
 

@@ -300,6 +300,49 @@ def test_batches_read_frame_and_mesh_replacement(cfg1):
         assert_views_match(r, tv2, tn2, tt2, tex, bases[:2])
 
 
+def test_state_carried_between_calls_is_clean():
+    """One context, many calls: frame slots and the direct pipeline's key buffer (left "no winner" by the resolve pass,
+    never cleared per batch) are reused by views whose screen regions differ and by calls with fewer views."""
+    rng = np.random.default_rng(404)
+    tv, tn, tt = random_soup(rng, 1500, size=(0.004, 0.03), xr=(-0.1, 0.5), yr=(0.2, 0.9), zspread=0.4)   # lopsided: the region moves with the view
+    tex = small_tex(rng, 64, 64)
+    views = [(0, 0), (0.5, 0.1), (-0.6, -0.1), (1.2, 0.05), (2.4, 0.0), (3.1, 0.1), (-1.5, 0.0), (0.2, 0.3)]
+    with make_renderer(480, 360, tv, tn, tt, tex) as r:
+        r.set_option("batch_views", 3)                                       # slots are reused inside one call, too
+        for order in (views, views[::-1], views[3:5], views[1:2], views):
+            bases = gel_b200.view_bases(order)
+            out = r.render(bases, z=True, hashes=True)
+            ref = oracle.render_views(tv, tn, tt, tex, 480, 360, bases, nthreads=NTHREADS, z=True, hashes=True)
+            assert out["rc"] == (1 if ref["clipped"] else 0)
+            assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"]))
+            assert np.array_equal(out["hash"], ref["hash"])
+
+
+def upright_rgb(canvas, xres, yres):
+    """Host restatement of the presentation step: schurn's -90 degree un-rotation (main.c:424-432; the same mapping as
+    gel_upright in gel_host.c) followed by dropping the X byte."""
+    up = canvas.reshape(xres, yres).T[::-1]                                 # up[wy, wx] = canvas[(yres-1-wy) + wx*yres]
+    return np.stack([(up >> 16) & 0xFF, (up >> 8) & 0xFF, up & 0xFF], axis=-1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("res", [(800, 600), (203, 97), (64, 32), (66, 35), (1, 1), (4, 3)])
+def test_frame_sink_rgb8(cfg1, res):
+    """gelcu_render_rgb8: upright 24-bit frames (word path when xres % 4 == 0, byte path otherwise) equal the host
+    transformation of the oracle's sideways frames; several batches so both frame buffers are used."""
+    tv, tn, tt, tex = cfg1
+    bases = gel_b200.view_bases([(0, 0), (0.4, 0.1), (2.0, 0.0), (-1.0, -0.05), (3.0, 0.2)])
+    with make_renderer(res[0], res[1], tv, tn, tt, tex) as r:
+        r.set_option("batch_views", 2)
+        out = r.render_rgb8(bases, hashes=True)
+        ref = oracle.render_views(tv, tn, tt, tex, res[0], res[1], bases, nthreads=NTHREADS, hashes=True)
+        assert out["rgb"].shape == (5, res[1], res[0], 3)
+        for k in range(5):
+            assert np.array_equal(out["rgb"][k], upright_rgb(ref["pixel"][k], res[0], res[1])), f"view {k}"
+        assert np.array_equal(out["hash"], ref["hash"])
+        again = r.render(bases, pixels=True)                                 # the plain path still works on the same context
+        assert np.array_equal(again["pixel"], ref["pixel"])
+
+
 def test_call_order_and_argument_errors():
     r = gel_b200.Renderer(64, 64)
     with pytest.raises(gel_b200.GelcuError) as e:
@@ -325,3 +368,19 @@ def test_headless_gel_matches_reference_output_format(cfg1_paths, golden):
     for f, l in zip(case["frames"], lines):
         assert l["fnv"] == f["fnv"] and l["nonzero"] == f["nonzero"] and l["checksum"] == f["salted_sum"]
     assert lines[-1]["summary"] and lines[-1]["views"] == 4
+
+
+def test_headless_gel_ppm_through_the_device_sink(cfg1_paths, tmp_path):
+    """`gel --ppm` writes the same files whether the host un-rotates and packs the XRGB frame (gel_write_ppm) or the
+    device does (--sink rgb8 -> gelcu_render_rgb8)."""
+    import json, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "gel_b200", "host", "gel")
+    common = [exe, *cfg1_paths, "--res", "320x200", "--frames", "3", "--mouse", "-50,7", "--batch", "2"]
+    a = subprocess.run([*common, "--ppm", str(tmp_path / "host")], capture_output=True, text=True, check=True).stdout
+    b = subprocess.run([*common, "--ppm", str(tmp_path / "dev"), "--sink", "rgb8"], capture_output=True, text=True, check=True).stdout
+    la, lb = ([json.loads(l) for l in o.splitlines() if l.startswith("{")] for o in (a, b))
+    for k in range(3):
+        assert la[k]["checksum"] == lb[k]["checksum"] and la[k]["nonzero"] == lb[k]["nonzero"]
+        host, dev = (open(tmp_path / f"{p}{k:04d}.ppm", "rb").read() for p in ("host", "dev"))
+        assert host == dev and host.startswith(b"P6\n320 200\n255\n") and len(host) == 15 + 320 * 200 * 3

@@ -97,13 +97,13 @@ def test_fnv_and_upright(cfg1):
 def test_abi_exports_every_declared_symbol():
     """libgelcu.so loads without a GPU and exports exactly the entry points include/gelcu.h declares."""
     hdr = open(os.path.join(ROOT, "include", "gelcu.h")).read()
-    declared = sorted(set(re.findall(r"^(?:int|void|const char\*)\s+(gelcu_[a-z_]+)\s*\(", hdr, re.M)))
+    declared = sorted(set(re.findall(r"^(?:int|void|const char\*)\s+(gelcu_[a-z0-9_]+)\s*\(", hdr, re.M)))
     assert declared == sorted(gel_b200.GELCU_SYMBOLS)
     L = gel_b200.cu()
     for s in declared:
         assert hasattr(L, s), s
     nm = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "gel_b200", "libgelcu.so")], capture_output=True, text=True).stdout
-    exported = sorted(set(re.findall(r" T (gelcu_[a-z_]+)", nm)))
+    exported = sorted(set(re.findall(r" T (gelcu_[a-z0-9_]+)", nm)))
     assert exported == declared
 
 
