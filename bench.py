@@ -280,15 +280,18 @@ def measure_gpu(r, name, inputs, views, steps, warmup, rank_offset, flush):
     return dev_ms, st, launches, stage, (t0, time.time())
 
 
-def measure_e2e(r, name, views, steps, warmup, rank_offset, pinned):
+def measure_e2e(r, name, views, steps, warmup, rank_offset, pinned, sink=False):
+    """sink=False: the drop-in call (sideways XRGB frames, 4 bytes per pixel over PCIe); sink=True: the device frame
+    sink (gelcu_render_rgb8: upright 24-bit frames, 3 bytes per pixel)."""
     import torch
     bases = [step_bases(name, views, rank_offset + s * views) for s in range(max(steps, warmup))]
+    call = (lambda b: r.render_rgb8(b, rgb_out=pinned.array[:views])) if sink else (lambda b: r.render(b, pixel_out=pinned.array[:views]))
     for s in range(min(warmup, 3)):
-        r.render(bases[s % len(bases)], pixel_out=pinned.array[:views])
+        call(bases[s % len(bases)])
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s in range(steps):
-        r.render(bases[s % len(bases)], pixel_out=pinned.array[:views])
+        call(bases[s % len(bases)])
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     st = r.stats()
@@ -382,6 +385,11 @@ def main():
     wall, est = measure_e2e(r, name, e2e_views, e2e_steps, args.warmup, rank_offset, pinned)
     e2e_fps = sum_over_ranks(e2e_views) * e2e_steps / max_over_ranks(wall)
     pinned.free()
+    # the same through the device frame sink: 24-bit upright frames, 25 % fewer PCIe bytes
+    pinned = gel_b200.PinnedBuffer((e2e_views, yres, xres, 3), np.uint8)
+    wall8, est8 = measure_e2e(r, name, e2e_views, e2e_steps, args.warmup, rank_offset, pinned, sink=True)
+    e2e8_fps = sum_over_ranks(e2e_views) * e2e_steps / max_over_ranks(wall8)
+    pinned.free()
 
     peak, peak_src = hbm_peak()
     launches_per_step_raster = st["batches"]
@@ -437,6 +445,8 @@ def main():
                          "dominant_kernel_alone": {"achieved": achieved, "frac": achieved / peak, "note": "B_alg x frames / the dominant kernel's time alone"}},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]),
                     "views_per_step_per_gpu": e2e_views, "note": "views from host, every frame's pixels copied to pinned host memory; PCIe-bound"},
+            "e2e_rgb8_sink": {"value": e2e8_fps, "unit": "frames/s", "h2d_bytes_per_step": int(est8["h2d_bytes"]), "d2h_bytes_per_step": int(est8["d2h_bytes"]),
+                              "note": "same, through gelcu_render_rgb8: frames un-rotated and packed to 24 bits on the device before the copy"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu:

@@ -482,7 +482,11 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         rc = ensure_work(c, B, cap_e, cap_d); if(rc) return rc;
         if(rgb_out && !c->d_rgb[0])
             for(int k = 0; k < 2; k++) CU(cudaMalloc(&c->d_rgb[k], 3 * frame * (size_t) c->batch));
-        const int nb = (nviews + c->batch - 1) / c->batch;
+        /* frames that go back to the host: a call is cut into at least four batches so that the copy of one batch
+         * runs under the rendering of the next (the copy is the longer of the two by an order of magnitude) */
+        int bsz = c->batch;
+        if((pixel_out || z_out || rgb_out) && c->batch_opt == 0) bsz = std::min(c->batch, std::max(8, (nviews + 3) / 4));
+        const int nb = (nviews + bsz - 1) / bsz;
         rc = ensure_events(c, nb); if(rc) return rc;
         c->stats.kernels_launched = 0; c->stats.h2d_bytes = 0; c->stats.d2h_bytes = 0; c->stats.batches = nb; c->stats.views = nviews;
         CU(cudaMemcpyAsync(c->d_views, views, sizeof(gelcu_view) * nviews, cudaMemcpyHostToDevice, c->stream));
@@ -498,7 +502,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         c->keys_dirty = true;
 
         auto issue_copies = [&](int b) -> int {
-            const int buf = b & 1, first = b * c->batch, n = std::min(c->batch, nviews - first);
+            const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
             CU(cudaStreamWaitEvent(c->copy_stream, c->render_done[buf], 0));
             if(pixel_out) { CU(cudaMemcpyAsync(pixel_out + frame * first, c->d_pixel[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
             if(z_out) { CU(cudaMemcpyAsync(z_out + frame * first, c->d_z[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
@@ -509,7 +513,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
 
         for(int b = 0; b < nb; b++)
         {
-            const int buf = b & 1, first = b * c->batch, n = std::min(c->batch, nviews - first);
+            const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
             rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, rgb_out != nullptr, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
             /* small per-batch results ride the render stream (the next batch overwrites their device copies) */
