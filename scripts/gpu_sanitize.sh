@@ -20,6 +20,11 @@ for pl in (1, 2):
         out = r.render(bases, z=True, hashes=True)
         ref = oracle.render_views(*mesh, tex, W, H, bases, nthreads=3, z=True, hashes=True)
         assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(out["hash"], ref["hash"]), (pl, W, H)
+        out = r.render(bases[::-1], z=True, hashes=True)                     # second call on the same context (key buffer restored by the resolve pass)
+        assert np.array_equal(out["pixel"], ref["pixel"][::-1]), (pl, W, H, "second call")
+        up = ref["pixel"][0].reshape(W, H).T[::-1]                           # frame sink: upright 24-bit frames
+        rgb = r.render_rgb8(bases)["rgb"]
+        assert np.array_equal(rgb[0], np.stack([(up >> 16) & 255, (up >> 8) & 255, up & 255], -1).astype(np.uint8)), (pl, W, H, "sink")
         r.close()
 print("sanitizer workload ok")
 PY
