@@ -141,8 +141,17 @@ static int draw_triangle(const float* vew, const float* nrm, const float* tex3,
             if(z > zbuff[y + x * yres])                               /* :356 */
             {
                 const float bc[3] = { v, w, u };
-                const int xx = (tw - 1) * (0.0f + (v * tex3[3] + w * tex3[6] + u * tex3[0]));   /* :360 */
-                const int yy = (th - 1) * (1.0f - (v * tex3[4] + w * tex3[7] + u * tex3[1]));   /* :361 */
+                int xx = (tw - 1) * (0.0f + (v * tex3[3] + w * tex3[6] + u * tex3[0]));         /* :360 */
+                int yy = (th - 1) * (1.0f - (v * tex3[4] + w * tex3[7] + u * tex3[1]));         /* :361 */
+                /* Outside [0,tw-1] x [0,th-1] the reference reads out of bounds (undefined).  Like the bbox clipping
+                 * above this restatement defines the case the way the product does -- clamp and flag (bit 2) -- so
+                 * that it stays a total function; in-domain inputs never come here. */
+                if(xx < 0 || xx > tw - 1 || yy < 0 || yy > th - 1)
+                {
+                    clipped |= 2;
+                    xx = xx < 0 ? 0 : xx > tw - 1 ? tw - 1 : xx;
+                    yy = yy < 0 ? 0 : yy > th - 1 ? th - 1 : yy;
+                }
                 const float intensity = dot3(bc, varying);            /* :362 */
                 const int shading = 0xFF * (intensity < 0.0f ? 0.0f : intensity > 1.0f ? 1.0f : intensity);
                 if(cnt) cnt->zpass++;

@@ -35,8 +35,10 @@ void ref_transform(const float* tv, const float* tn, int ntri, const float basis
 
 /* one frame: reset + transform + raster                   main.c:505-522
  * tv/tn/tt: 9 floats per triangle; tex: XRGB8888 top-down tw x th; pixel/zbuff: xres*yres, index y + x*yres.
- * Returns 0, or 1 if any triangle's bbox left [0,xres-1]x[0,yres-1] (such triangles are SKIPPED whole
- * pixels-wise outside the screen -- the reference would write out of bounds there). */
+ * Returns 0 for in-domain input, else flag bits for the two cases where the reference itself is undefined (it would
+ * access memory out of bounds); this restatement defines both the way the product does, so the two stay comparable:
+ *   1  a triangle's bbox left [0,xres-1]x[0,yres-1]: the bbox is clipped to the screen        
+ *   2  a texel coordinate left [0,tw-1]x[0,th-1]: it is clamped                                (main.c:360-366) */
 int ref_render(const float* tv, const float* tn, const float* tt, int ntri,
                const uint32_t* tex, int tw, int th, int xres, int yres, const float basis[12],
                uint32_t* pixel, float* zbuff, RefCounters* counters);

@@ -280,8 +280,11 @@ def test_texel_out_of_range_is_clamped_and_flagged():
     tn = np.array([[0, 0, 1] * 3], np.float32)
     tt = np.array([[0, 0, 0, 1.5, 0, 0, 0, 1.5, 0]], np.float32)
     with make_renderer(320, 240, tv, tn, tt, small_tex(np.random.default_rng(1))) as r:
-        out = r.render(gel_b200.view_bases([(0, 0)]))
+        bases = gel_b200.view_bases([(0, 0)])
+        out = r.render(bases, z=True)
         assert out["rc"] == gel_b200.GELCU_W_CLIPPED and r.stats()["flags"] & 2
+        ref = oracle.render_views(tv, tn, tt, small_tex(np.random.default_rng(1)), 320, 240, bases, z=True)   # the oracle defines the case the same way
+        assert ref["clipped"] & 2 and np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"]))
 
 
 def test_batches_read_frame_and_mesh_replacement(cfg1):
@@ -384,3 +387,14 @@ def test_headless_gel_ppm_through_the_device_sink(cfg1_paths, tmp_path):
         assert la[k]["checksum"] == lb[k]["checksum"] and la[k]["nonzero"] == lb[k]["nonzero"]
         host, dev = (open(tmp_path / f"{p}{k:04d}.ppm", "rb").read() for p in ("host", "dev"))
         assert host == dev and host.startswith(b"P6\n320 200\n255\n") and len(host) == 15 + 320 * 200 * 3
+
+
+def test_differential_fuzz_sample(monkeypatch):
+    """A slice of scripts/gpu_fuzz.py (adversarial random scenes: slivers, sub-pixel and screen-filling triangles,
+    duplicates, coplanar stacks, off-screen and out-of-texture inputs; both pipelines, two calls per context)."""
+    import importlib.util, sys
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("gpu_fuzz", os.path.join(ROOT, "scripts", "gpu_fuzz.py"))
+    fuzz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fuzz)
+    monkeypatch.setattr(sys, "argv", ["gpu_fuzz.py", "24", "1000"])
+    assert fuzz.main() == 0
