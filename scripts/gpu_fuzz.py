@@ -26,7 +26,7 @@ def scene(rng):
         tt = np.zeros((n, 3, 3)); tt[:, :, :2] = rng.uniform(*uvr, (n, 3, 2))
         parts_v.append(tv.reshape(n, 9)); parts_n.append(tn.reshape(n, 9)); parts_t.append(tt.reshape(n, 9))
 
-    kinds = rng.integers(0, 2, 8)
+    kinds = rng.integers(0, 2, 9)
     wide = rng.integers(0, 2)
     add(int(rng.integers(50, 2500)), (0.002, 0.03), (-0.5, 0.5) if wide else (-0.2, 0.2), (0.0, 1.0) if wide else (0.3, 0.7), (-0.3, 0.3) if wide else (-0.15, 0.15))   # small
     if kinds[0] and wide: add(int(rng.integers(1, 30)), (0.3, 1.5), (-0.3, 0.3), (0.2, 0.8), (-0.2, 0.2))          # huge, some off screen
@@ -34,6 +34,7 @@ def scene(rng):
     if kinds[2]: add(int(rng.integers(10, 300)), (0.01, 0.1), (-0.2, 0.2), (0.3, 0.7), (0.0, 0.0))        # coplanar (z = 0 before view)
     if kinds[3] and wide: add(int(rng.integers(5, 100)), (0.01, 0.2), (-0.9, 0.9), (-0.4, 1.4), (-0.3, 0.3))       # crossing the screen edges
     if kinds[4] and wide: add(int(rng.integers(5, 100)), (0.01, 0.1), (-0.2, 0.2), (0.3, 0.7), (-0.15, 0.15), uvr=(-0.3, 1.3))   # texel out of range
+    if kinds[8] and wide: add(int(rng.integers(1, 12)), (5.0, 400.0), (-0.3, 0.3), (0.2, 0.8), (-0.05, 0.05))        # giant: edges of 1e3..1e5 px, den beyond the guard range
     tv, tn, tt = (np.vstack(p).astype(np.float32) for p in (parts_v, parts_n, parts_t))
     n = tv.shape[0]
     if kinds[5]:                                                                                           # exact duplicates, different uv
