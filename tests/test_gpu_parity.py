@@ -398,3 +398,21 @@ def test_differential_fuzz_sample(monkeypatch):
     fuzz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fuzz)
     monkeypatch.setattr(sys, "argv", ["gpu_fuzz.py", "24", "1000"])
     assert fuzz.main() == 0
+
+
+def test_maximum_resolution_8192():
+    """The largest frame the ABI accepts (8192 x 8192, 13-bit coordinates in the packed records): two views, small and
+    screen-sized triangles, through the oracle's own full-size render."""
+    rng = np.random.default_rng(8192)
+    tv, tn, tt = random_soup(rng, 400, size=(0.002, 0.05), xr=(-0.4, 0.4), yr=(0.1, 0.9))
+    bv, bn, bt = random_soup(rng, 6, size=(0.3, 0.6), xr=(-0.2, 0.2), yr=(0.3, 0.7))
+    tv, tn, tt = np.vstack([tv, bv]), np.vstack([tn, bn]), np.vstack([tt, bt])
+    tex = small_tex(rng, 64, 64)
+    bases = gel_b200.view_bases([(0.1, 0.05), (3.0, -0.1)])
+    with make_renderer(8192, 8192, tv, tn, tt, tex) as r:
+        out = r.render(bases, z=True, hashes=True)
+        ref = oracle.render_views(tv, tn, tt, tex, 8192, 8192, bases, nthreads=2, z=True, hashes=True)
+        assert out["rc"] == (1 if ref["clipped"] else 0)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"]))
+        assert np.array_equal(out["hash"], ref["hash"])
+        assert int((ref["pixel"] != 0).sum()) > 1_000_000
