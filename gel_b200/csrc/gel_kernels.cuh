@@ -36,11 +36,17 @@ constexpr int TH = 32;             /* tile height (screen y, contiguous in memor
 #endif
 constexpr int RASTER_THREADS = GEL_RASTER_THREADS;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int FRAG_MAX = 256;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
+#ifndef GEL_FRAG_MAX
+#define GEL_FRAG_MAX 256
+#endif
+#ifndef GEL_TWO_PHASE_MIN
+#define GEL_TWO_PHASE_MIN 128
+#endif
+constexpr int FRAG_MAX = GEL_FRAG_MAX;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
 constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
 constexpr int QCAP = 64;           /* survivor stack per warp: < 32 left over + one row of 32 lanes       */
 constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16 B each, global scratch)   */
-constexpr int TWO_PHASE_MIN = 128;  /* tiles with fewer entries are rasterised in one phase                */
+constexpr int TWO_PHASE_MIN = GEL_TWO_PHASE_MIN;  /* tiles with fewer entries are rasterised in one phase                */
 constexpr int MAX_BATCH = 256;     /* views per launch set (K3 keeps a per-view prefix in shared memory)  */
 constexpr int DEFER_MAX = 256;     /* large triangles per round left to the CTA-wide sweep                */
 constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
