@@ -39,7 +39,8 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #define GEL_DIRECT_TPW 1024
 #endif
 constexpr int RESOLVE_WCOLS = GEL_RESOLVE_WCOLS;
-constexpr int TREC_QUADS = 4;                    /* 64-byte static record per triangle for the resolve pass */
+constexpr int TREC_QUADS = 4;                    /* wide static record per triangle for the resolve pass: 64 bytes */
+constexpr int TREC_COMPACT_BITS = 21;            /* meshes with < 2^21 distinct vertices: 32-byte record, three 21-bit indices */
 constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
 constexpr int DIRECT_UNIT_WINDOW = 256;
@@ -53,7 +54,7 @@ constexpr int VSTAT = VIEW_STAT_WORDS;             /* per-view words: zlo, zhi, 
 
 struct DirectParams
 {
-    const float4* xf; const uint32_t *i0, *i1, *i2; const uint4* trec;   /* trec: TREC_QUADS x 16 bytes per triangle: {i0,i1,i2,-} {u0,v0,u1,v1} {u2,v2,-,-} */
+    const float4* xf; const uint32_t *i0, *i1, *i2; const uint4* trec;   /* per triangle, wide: 4 x 16 bytes {i0,i1,i2,-} {u0,v0,u1,v1} {u2,v2,-,-} -;  compact: 2 x 16 bytes {i0 | i1 << 21 | i2 << 42 (64 bits), u0, v0} {u1,v1,u2,v2} */
     const uint32_t* tex; int tw, th;
     unsigned long long* keys;      /* [view][xres*yres]  index y + x*yres                                   */
     uint32_t* hiz;                 /* [view][hbx*hby]    min depth key per 8x8 block, index bx*hby + by     */
@@ -397,6 +398,7 @@ direct_raster_kernel(DirectParams p)
 
 /* D5 ------------------------------------------------------------------------------------------------------------ */
 /* one pixel: the winner's barycentrics recomputed from the same operands (identical bits), shaded once */
+template<bool COMPACT>
 __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, unsigned long long key, int x, int y, uint32_t& colour, float& z)
 {
     colour = 0u; z = -FLT_MAX;
@@ -404,11 +406,25 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float4* xf = p.xf + (size_t) view * p.nuniq;
     const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
     z = gel::zkey_inv((uint32_t) (key >> 32));
-    const uint4* rec = p.trec + (size_t) TREC_QUADS * tri;
-    const uint4 ri = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-    const float4 a = __ldg(xf + ri.x);
-    const float4 b = __ldg(xf + ri.y);
-    const float4 c = __ldg(xf + ri.z);
+    uint32_t ia, ib, ic, uvw[6];
+    if(COMPACT)
+    {
+        const uint4* rec = p.trec + 2 * (size_t) tri;
+        const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        const uint32_t m = (1u << TREC_COMPACT_BITS) - 1u;
+        ia = r0.x & m; ib = (r0.x >> 21 | r0.y << 11) & m; ic = (r0.y >> 10) & m;
+        uvw[0] = r0.z; uvw[1] = r0.w; uvw[2] = r1.x; uvw[3] = r1.y; uvw[4] = r1.z; uvw[5] = r1.w;
+    }
+    else
+    {
+        const uint4* rec = p.trec + (size_t) TREC_QUADS * tri;
+        const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        ia = r0.x; ib = r0.y; ic = r0.z;
+        uvw[0] = r1.x; uvw[1] = r1.y; uvw[2] = r1.z; uvw[3] = r1.w; uvw[4] = r2.x; uvw[5] = r2.y;
+    }
+    const float4 a = __ldg(xf + ia);
+    const float4 b = __ldg(xf + ib);
+    const float4 c = __ldg(xf + ic);
     /* tbarycenter at this pixel (main.c:316-332), same operations and operands as the visibility pass */
     const float v0x = gel::sub(b.x, a.x), v0y = gel::sub(b.y, a.y), v0z = gel::sub(b.z, a.z);
     const float v1x = gel::sub(c.x, a.x), v1y = gel::sub(c.y, a.y), v1z = gel::sub(c.z, a.z);
@@ -420,7 +436,7 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float v = gel::dvd(gel::sub(gel::mul(d11, d20), gel::mul(d01, d21)), den);
     const float w = gel::dvd(gel::sub(gel::mul(d00, d21), gel::mul(d01, d20)), den);
     const float u = gel::sub(gel::sub(1.0f, v), w);
-    const float uv[6] = { __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w), __uint_as_float(r2.x), __uint_as_float(r2.y) };
+    const float uv[6] = { __uint_as_float(uvw[0]), __uint_as_float(uvw[1]), __uint_as_float(uvw[2]), __uint_as_float(uvw[3]), __uint_as_float(uvw[4]), __uint_as_float(uvw[5]) };
     int xx, yy, shading;
     gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
     if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
@@ -470,7 +486,7 @@ direct_fill_kernel(DirectParams p)
  * compact footprint is what keeps the gathers cheap: a warp's 32 pixels then touch few distinct triangles, vertices
  * and -- above all -- texture rows (a 1 x 32 column touched ~30 texture lines per texel load, the L1 data pipe was
  * the kernel's limit), and neighbouring warps reuse the same lines out of L1. */
-template<bool HASH>
+template<bool HASH, bool COMPACT>
 __global__ void __launch_bounds__(256, GEL_RESOLVE_MINB)
 direct_resolve_kernel(DirectParams p)
 {
@@ -492,7 +508,7 @@ direct_resolve_kernel(DirectParams p)
             const unsigned long long key = next_key;
             if(y + CTA_ROWS <= ry1) next_key = p.keys[base + y + CTA_ROWS];   /* one iteration ahead of its use */
             uint32_t colour; float z;
-            direct_shade(p, view, key, x, y, colour, z);
+            direct_shade<COMPACT>(p, view, key, x, y, colour, z);
             p.keys[base + y] = CLEAR_KEY;                                 /* the buffer is all "no winner" again for the next batch */
             p.pixel[base + y] = colour;
             p.zbuf[base + y] = z;

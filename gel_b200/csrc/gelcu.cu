@@ -48,7 +48,7 @@ struct gelcu_ctx
     cudaEvent_t side_go = nullptr, side_done = nullptr;
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
-    float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr;
+    float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr; bool trec_compact = false, allow_compact = true;
     /* texture */
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
@@ -196,8 +196,9 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             direct_raster_kernel<1><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched += 2;
         }
-        if(want_hash) direct_resolve_kernel<true><<<dim3(RESOLVE_CTAS, n), 256, 0, s>>>(dp);
-        else direct_resolve_kernel<false><<<dim3(RESOLVE_CTAS, n), 256, 0, s>>>(dp);
+        const dim3 sgrid(RESOLVE_CTAS, n);
+        if(c->trec_compact) { if(want_hash) direct_resolve_kernel<true, true><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, true><<<sgrid, 256, 0, s>>>(dp); }
+        else { if(want_hash) direct_resolve_kernel<true, false><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, false><<<sgrid, 256, 0, s>>>(dp); }
         c->stats.kernels_launched++;
         CU(cudaStreamWaitEvent(s, c->side_done, 0));
     }
@@ -390,14 +391,25 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
 
     /* the direct pipeline's resolve pass gathers per winning pixel: one 64-byte record per triangle (vertex indices +
      * texture coordinates) costs three 16-byte loads in one cache line instead of six loads in four arrays */
-    std::vector<uint4> trec((size_t) TREC_QUADS * ntri, make_uint4(0u, 0u, 0u, 0u));
+    const bool compact = c->allow_compact && vpos.size() < ((size_t) 1 << TREC_COMPACT_BITS);   /* three 21-bit indices fit one 64-bit word: 32-byte record */
+    const int quads = compact ? 2 : TREC_QUADS;
+    std::vector<uint4> trec((size_t) quads * ntri, make_uint4(0u, 0u, 0u, 0u));
     for(int t = 0; t < ntri; t++)
     {
         uint32_t w[8];
         memcpy(w, &uv[3 * (size_t) t], 24);
-        trec[(size_t) TREC_QUADS * t] = make_uint4(idx[0][t], idx[1][t], idx[2][t], 0u);
-        trec[(size_t) TREC_QUADS * t + 1] = make_uint4(w[0], w[1], w[2], w[3]);
-        trec[(size_t) TREC_QUADS * t + 2] = make_uint4(w[4], w[5], 0u, 0u);
+        if(compact)
+        {
+            const unsigned long long packed = (unsigned long long) idx[0][t] | (unsigned long long) idx[1][t] << 21 | (unsigned long long) idx[2][t] << 42;
+            trec[2 * (size_t) t] = make_uint4((uint32_t) packed, (uint32_t) (packed >> 32), w[0], w[1]);
+            trec[2 * (size_t) t + 1] = make_uint4(w[2], w[3], w[4], w[5]);
+        }
+        else
+        {
+            trec[(size_t) TREC_QUADS * t] = make_uint4(idx[0][t], idx[1][t], idx[2][t], 0u);
+            trec[(size_t) TREC_QUADS * t + 1] = make_uint4(w[0], w[1], w[2], w[3]);
+            trec[(size_t) TREC_QUADS * t + 2] = make_uint4(w[4], w[5], 0u, 0u);
+        }
     }
 
     free_work(c);
@@ -407,7 +419,8 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
     CU(cudaMalloc(&c->d_vpos, sizeof(float4) * nu)); CU(cudaMalloc(&c->d_vnrm, sizeof(float4) * nu));
     CU(cudaMalloc(&c->d_i0, 4 * nt)); CU(cudaMalloc(&c->d_i1, 4 * nt)); CU(cudaMalloc(&c->d_i2, 4 * nt));
     CU(cudaMalloc(&c->d_uv, sizeof(float2) * 3 * nt));
-    CU(cudaMalloc(&c->d_trec, sizeof(uint4) * TREC_QUADS * nt));
+    CU(cudaMalloc(&c->d_trec, sizeof(uint4) * std::max<size_t>(1, trec.size())));
+    c->trec_compact = compact;
     if(ntri > 0)
     {
         CU(cudaMemcpy(c->d_vpos, vpos.data(), sizeof(float4) * vpos.size(), cudaMemcpyHostToDevice));
@@ -440,6 +453,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
+    else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
     else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
     return GELCU_OK;

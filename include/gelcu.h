@@ -111,7 +111,9 @@ int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out
  *   "batch_views"   views rendered per kernel launch set (default: sized so frames fit ~8 GB)
  *   "raster_ctas_per_sm"   persistent rasteriser CTAs per SM, 1..16 (default: 1024 threads per SM)
  *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1)
- *   "pipeline"      0 = chosen from the mesh (default), 1 = tile pipeline, 2 = direct pipeline */
+ *   "pipeline"      0 = chosen from the mesh (default), 1 = tile pipeline, 2 = direct pipeline
+ *   "compact_records"  1 (default) = meshes with fewer than 2^21 distinct vertices get 32-byte per-triangle shading
+ *                   records (three 21-bit indices), 0 = always the 64-byte form; read by the next gelcu_set_mesh */
 int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
 int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
 

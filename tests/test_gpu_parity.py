@@ -346,6 +346,20 @@ def test_frame_sink_rgb8(cfg1, res):
         assert np.array_equal(again["pixel"], ref["pixel"])
 
 
+def test_wide_and_compact_shading_records_agree(cfg1):
+    """The direct pipeline's resolve pass reads one static record per triangle: 32 bytes when the mesh has fewer than 2^21
+    distinct vertices, 64 bytes otherwise.  Force each form on the same mesh."""
+    tv, tn, tt, tex = cfg1
+    bases = gel_b200.view_bases([(0, 0), (1.3, 0.1)])
+    ref = oracle.render_views(tv, tn, tt, tex, 400, 300, bases, nthreads=NTHREADS, z=True, hashes=True)
+    for compact in (0, 1):
+        with gel_b200.Renderer(400, 300) as r:
+            r.set_option("compact_records", compact)
+            r.set_mesh(tv, tn, tt); r.set_texture(tex); r.set_option("pipeline", 2)
+            out = r.render(bases, z=True, hashes=True)
+            assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])) and np.array_equal(out["hash"], ref["hash"])
+
+
 def test_call_order_and_argument_errors():
     r = gel_b200.Renderer(64, 64)
     with pytest.raises(gel_b200.GelcuError) as e:
