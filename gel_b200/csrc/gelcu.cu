@@ -81,9 +81,9 @@ void free_work(gelcu_ctx* c)
 }
 
 #ifndef GEL_RESOLVE_CTAS
-#define GEL_RESOLVE_CTAS 128
+#define GEL_RESOLVE_CTAS 1024
 #endif
-constexpr int RESOLVE_CTAS = GEL_RESOLVE_CTAS;  /* CTAs per view in the direct pipeline's resolve pass (each walks strips of 8 columns) */
+constexpr int RESOLVE_CTAS = GEL_RESOLVE_CTAS;  /* most CTAs per view in the direct pipeline's resolve pass (each walks strips of 8 columns) */
 constexpr int EV_PER_BATCH = 5;   /* start, after K1, after bin/clear, after the dominant raster kernel, end */
 
 int active_pipeline(const gelcu_ctx* c) { return c->pipeline_opt ? c->pipeline_opt : c->pipeline_auto; }
@@ -196,7 +196,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             direct_raster_kernel<1><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched += 2;
         }
-        const dim3 sgrid(RESOLVE_CTAS, n);
+        const dim3 sgrid(std::min(RESOLVE_CTAS, (c->xres + 7) / 8), n);   /* one strip of 8 columns per CTA when the grid allows; CTAs past the region's last strip exit at once */
         if(c->trec_compact) { if(want_hash) direct_resolve_kernel<true, true><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, true><<<sgrid, 256, 0, s>>>(dp); }
         else { if(want_hash) direct_resolve_kernel<true, false><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, false><<<sgrid, 256, 0, s>>>(dp); }
         c->stats.kernels_launched++;
