@@ -29,6 +29,9 @@ namespace gelk {
 #endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
+#ifndef GEL_ZSPLIT
+#define GEL_ZSPLIT 0.4f           /* near / far split of a view, as a fraction of its depth range (any value is exact; this one is a speed heuristic) */
+#endif
 #ifndef GEL_RESOLVE_WCOLS
 #define GEL_RESOLVE_WCOLS 4        /* columns of a resolve warp's pixel footprint (x 32/WCOLS rows); 1, 2, 4 or 8 */
 #endif
@@ -112,7 +115,7 @@ direct_clear_kernel(DirectParams p)
         const uint32_t* s = p.vstat + (size_t) view * VSTAT;
         const float lo = gel::zkey_inv(s[0]), hi = gel::zkey_inv(s[1]);
         r[0] = any ? x0 : 0; r[1] = any ? x1 : -1; r[2] = any ? y0 : 0; r[3] = any ? y1 : -1;
-        r[4] = __float_as_int(lo + 0.5f * (hi - lo));          /* near / far split of the view */
+        r[4] = __float_as_int(lo + GEL_ZSPLIT * (hi - lo));          /* near / far split of the view */
     }
 }
 
