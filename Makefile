@@ -19,7 +19,7 @@ gel_b200/libgelcu.so: $(wildcard gel_b200/csrc/*) include/gelcu.h
 	$(NVCC) $(NVFLAGS) -shared gel_b200/csrc/gelcu.cu -o $@
 
 gel_b200/libgelhost.so: gel_b200/host/gel_host.c gel_b200/host/gel_host.h
-	$(CC) $(CSTRICT) -shared gel_b200/host/gel_host.c -o $@ -lm
+	$(CC) $(CSTRICT) -shared -pthread gel_b200/host/gel_host.c -o $@ -lm
 
 gel_b200/host/gel: gel_b200/host/gel.c gel_b200/host/gel_host.c gel_b200/host/gel_host.h include/gelcu.h gel_b200/libgelcu.so
 	$(CC) $(CSTRICT) -Iinclude gel_b200/host/gel.c gel_b200/host/gel_host.c -o $@ \

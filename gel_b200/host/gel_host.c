@@ -10,9 +10,11 @@
 #include "gel_host.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 typedef struct { float* p; size_t n, cap; } FVec;
 typedef struct { int* p; size_t n, cap; } IVec;
@@ -74,6 +76,64 @@ static int scan_face(const char* s, int* q)
     return got;
 }
 
+/* one chunk of the file: whole lines in [begin, end) */
+enum { PARSE_MAX_THREADS = 32 };
+typedef struct { char* begin; char* end; FVec vs, ns, ts; IVec fs; int rc; } ParseJob;
+
+static void* parse_chunk(void* arg)
+{
+    ParseJob* j = (ParseJob*) arg;
+    int rc = 0;
+    for(char* line = j->begin; line < j->end && rc == 0; )
+    {
+        char* nl = (char*) memchr(line, '\n', (size_t) (j->end - line));
+        if(nl) *nl = '\0';
+        float v[3];
+        if(line[0] == 'v' && line[1] == 'n') { scan3f(line + 2, v); rc = fvec_push3(&j->ns, v); }
+        else if(line[0] == 'v' && line[1] == 't') { scan3f(line + 2, v); rc = fvec_push3(&j->ts, v); }
+        else if(line[0] == 'v') { scan3f(line + 1, v); rc = fvec_push3(&j->vs, v); }
+        else if(line[0] == 'f')
+        {
+            int q[9];
+            if(scan_face(line + 1, q) == 9)
+            {
+                for(int k = 0; k < 9; k++) q[k] -= 1;
+                rc = ivec_push9(&j->fs, q);
+            }
+            else rc = -2;
+        }
+        if(!nl) break;
+        line = nl + 1;
+    }
+    j->rc = rc;
+    return NULL;
+}
+
+typedef struct
+{
+    const float *vs, *ns, *ts; const int* fs; int nv, nvt, nvn; float inv;
+    float *tv, *tn, *tt; int first, last, rc;
+}
+ExpandJob;
+
+static void* expand_range(void* arg)
+{
+    ExpandJob* j = (ExpandJob*) arg;
+    for(int i = j->first; i < j->last; i++)
+        for(int k = 0; k < 3; k++)
+        {
+            const int* q = j->fs + 9 * (size_t) i + 3 * k;   /* v, t, n of corner k */
+            if(q[0] < 0 || q[0] >= j->nv || q[1] < 0 || q[1] >= j->nvt || q[2] < 0 || q[2] >= j->nvn) { j->rc = -2; return NULL; }
+            for(int e = 0; e < 3; e++)
+            {
+                j->tv[9 * (size_t) i + 3 * k + e] = j->vs[3 * q[0] + e] * j->inv;
+                j->tt[9 * (size_t) i + 3 * k + e] = j->ts[3 * q[1] + e];
+                j->tn[9 * (size_t) i + 3 * k + e] = j->ns[3 * q[2] + e];
+            }
+        }
+    return NULL;
+}
+
 int gel_obj_load(const char* path, GelMesh* out)
 {
     memset(out, 0, sizeof *out);
@@ -88,31 +148,63 @@ int gel_obj_load(const char* path, GelMesh* out)
     fclose(f);
     text[got] = '\0';
 
+    /* Large files are cut into chunks at line boundaries and parsed by several threads; the
+     * pieces are joined in file order, so the arrays are the ones a single pass produces. */
+    int nthreads = 1;
+    if(got >= ((size_t) 4 << 20))
+    {
+        const char* env = getenv("GEL_PARSE_THREADS");
+        long want = env ? strtol(env, NULL, 10) : sysconf(_SC_NPROCESSORS_ONLN);
+        nthreads = want < 1 ? 1 : want > PARSE_MAX_THREADS ? PARSE_MAX_THREADS : (int) want;
+    }
+    ParseJob jobs[PARSE_MAX_THREADS];
+    pthread_t tid[PARSE_MAX_THREADS];
+    memset(jobs, 0, sizeof jobs);
+    char* cut = text;
+    for(int t = 0; t < nthreads; t++)
+    {
+        char* end = t == nthreads - 1 ? text + got : text + got / (size_t) nthreads * (size_t) (t + 1);
+        if(end < cut) end = cut;
+        if(t != nthreads - 1)
+        {
+            char* nl = (char*) memchr(end, '\n', (size_t) (text + got - end));      /* a chunk ends after a newline */
+            end = nl ? nl + 1 : text + got;
+        }
+        jobs[t].begin = cut; jobs[t].end = end;
+        cut = end;
+    }
+    int spawned = 0;
+    for(int t = 1; t < nthreads; t++)
+    {
+        if(pthread_create(&tid[t], NULL, parse_chunk, &jobs[t]) != 0) break;
+        spawned = t;
+    }
+    for(int t = spawned + 1; t < nthreads; t++) parse_chunk(&jobs[t]);              /* threads that could not start: inline */
+    parse_chunk(&jobs[0]);
+    for(int t = 1; t <= spawned; t++) pthread_join(tid[t], NULL);
+    free(text);
+
     FVec vs = { 0 }, ns = { 0 }, ts = { 0 };
     IVec fs = { 0 };
     int rc = 0;
-    for(char* line = text; line < text + got && rc == 0; )
+    for(int t = 0; t < nthreads; t++) if(jobs[t].rc) rc = jobs[t].rc;
+    if(rc == 0 && nthreads == 1) { vs = jobs[0].vs; ns = jobs[0].ns; ts = jobs[0].ts; fs = jobs[0].fs; memset(&jobs[0], 0, sizeof jobs[0]); }
+    else if(rc == 0)
     {
-        char* nl = (char*) memchr(line, '\n', (size_t) (text + got - line));
-        if(nl) *nl = '\0';
-        float v[3];
-        if(line[0] == 'v' && line[1] == 'n') { scan3f(line + 2, v); rc = fvec_push3(&ns, v); }
-        else if(line[0] == 'v' && line[1] == 't') { scan3f(line + 2, v); rc = fvec_push3(&ts, v); }
-        else if(line[0] == 'v') { scan3f(line + 1, v); rc = fvec_push3(&vs, v); }
-        else if(line[0] == 'f')
+        size_t nvs = 0, nns = 0, nts = 0, nfs = 0;
+        for(int t = 0; t < nthreads; t++) { nvs += jobs[t].vs.n; nns += jobs[t].ns.n; nts += jobs[t].ts.n; nfs += jobs[t].fs.n; }
+        vs.p = (float*) malloc(sizeof(float) * (nvs ? nvs : 1)); ns.p = (float*) malloc(sizeof(float) * (nns ? nns : 1));
+        ts.p = (float*) malloc(sizeof(float) * (nts ? nts : 1)); fs.p = (int*) malloc(sizeof(int) * (nfs ? nfs : 1));
+        if(!vs.p || !ns.p || !ts.p || !fs.p) rc = -3;
+        for(int t = 0; t < nthreads && rc == 0; t++)
         {
-            int q[9];
-            if(scan_face(line + 1, q) == 9)
-            {
-                for(int k = 0; k < 9; k++) q[k] -= 1;
-                rc = ivec_push9(&fs, q);
-            }
-            else rc = -2;
+            memcpy(vs.p + vs.n, jobs[t].vs.p, sizeof(float) * jobs[t].vs.n); vs.n += jobs[t].vs.n;
+            memcpy(ns.p + ns.n, jobs[t].ns.p, sizeof(float) * jobs[t].ns.n); ns.n += jobs[t].ns.n;
+            memcpy(ts.p + ts.n, jobs[t].ts.p, sizeof(float) * jobs[t].ts.n); ts.n += jobs[t].ts.n;
+            memcpy(fs.p + fs.n, jobs[t].fs.p, sizeof(int) * jobs[t].fs.n); fs.n += jobs[t].fs.n;
         }
-        if(!nl) break;
-        line = nl + 1;
     }
-    free(text);
+    for(int t = 0; t < nthreads; t++) { free(jobs[t].vs.p); free(jobs[t].ns.p); free(jobs[t].ts.p); free(jobs[t].fs.p); }
     if(rc) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return rc == -2 ? -2 : -3; }
 
     const int nv = (int) (vs.n / 3), nvn = (int) (ns.n / 3), nvt = (int) (ts.n / 3), nt = (int) (fs.n / 9);
@@ -127,22 +219,33 @@ int gel_obj_load(const char* path, GelMesh* out)
     const int scale = (int) maxlen;
     if(nt > 0 && scale == 0) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return -4; }
     const float inv = nt > 0 ? 1.0f / scale : 1.0f;
-    out->tv = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
-    out->tn = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
-    out->tt = (float*) malloc(sizeof(float) * 9 * (size_t) (nt ? nt : 1));
+    const size_t soup_tris = nt > 0 ? (size_t) nt : 1;
+    out->tv = (float*) malloc(sizeof(float) * 9 * soup_tris);
+    out->tn = (float*) malloc(sizeof(float) * 9 * soup_tris);
+    out->tt = (float*) malloc(sizeof(float) * 9 * soup_tris);
     if(!out->tv || !out->tn || !out->tt) rc = -3;
-    for(int i = 0; i < nt && rc == 0; i++)
-        for(int k = 0; k < 3; k++)
+    if(rc == 0)
+    {
+        /* soup expansion (tvgen / ttgen / tngen, main.c:242-286): triangle ranges are independent */
+        ExpandJob ej[PARSE_MAX_THREADS];
+        const int nexp = nt >= (1 << 16) ? nthreads : 1;
+        for(int t = 0; t < nexp; t++)
         {
-            const int* q = fs.p + 9 * (size_t) i + 3 * k;   /* v, t, n of corner k */
-            if(q[0] < 0 || q[0] >= nv || q[1] < 0 || q[1] >= nvt || q[2] < 0 || q[2] >= nvn) { rc = -2; break; }
-            for(int e = 0; e < 3; e++)
-            {
-                out->tv[9 * (size_t) i + 3 * k + e] = vs.p[3 * q[0] + e] * inv;
-                out->tt[9 * (size_t) i + 3 * k + e] = ts.p[3 * q[1] + e];
-                out->tn[9 * (size_t) i + 3 * k + e] = ns.p[3 * q[2] + e];
-            }
+            ExpandJob e = { vs.p, ns.p, ts.p, fs.p, nv, nvt, nvn, inv, out->tv, out->tn, out->tt,
+                            (int) ((long long) nt * t / nexp), (int) ((long long) nt * (t + 1) / nexp), 0 };
+            ej[t] = e;
         }
+        int started = 0;
+        for(int t = 1; t < nexp; t++)
+        {
+            if(pthread_create(&tid[t], NULL, expand_range, &ej[t]) != 0) break;
+            started = t;
+        }
+        for(int t = started + 1; t < nexp; t++) expand_range(&ej[t]);
+        expand_range(&ej[0]);
+        for(int t = 1; t <= started; t++) pthread_join(tid[t], NULL);
+        for(int t = 0; t < nexp; t++) if(ej[t].rc) rc = ej[t].rc;
+    }
     free(vs.p); free(ns.p); free(ts.p); free(fs.p);
     if(rc) { gel_mesh_free(out); return rc; }
     out->ntri = nt; out->nv = nv; out->nvt = nvt; out->nvn = nvn;

@@ -1,7 +1,8 @@
 /* gel_host.h -- host-side C flow around the render path: the parts of the reference's main.c that stay on
  * the CPU when lines 505-522 move to the GPU.  Pure C99, no CUDA, no SDL.
  *
- *   gel_obj_load      oload + oparse + tvgen/ttgen/tngen     main.c:460-469, 84-180, 227-286
+ *   gel_obj_load      oload + oparse + tvgen/ttgen/tngen     main.c:460-469, 84-180, 227-286   (files > 4 MB: parsed in
+ *                     line-aligned chunks by up to 32 threads, GEL_PARSE_THREADS overrides; same arrays as one pass)
  *   gel_bmp_load      sload (IMG_Load + convert to RGB888)    main.c:471-484   (24-bit BMP only, no SDL_image)
  *   gel_view_basis    camera basis from (xt, yt)              main.c:506-512
  *   gel_input_step    ipump's angle update                    main.c:408-409

@@ -49,6 +49,27 @@ def test_obj_errors(tmp_path):
         gel_b200.load_obj(str(small))
 
 
+def test_parallel_obj_parse_is_identical(tmp_path, monkeypatch):
+    """Files above 4 MB are parsed in chunks by several threads: same soups for every thread
+    count, equal to the reference-style loader; a bad face in a late chunk is still an error."""
+    from gel_b200 import synth
+    text = synth.sphere_obj_text(150, 150)                                  # 45 000 triangles, ~4.9 MB
+    assert len(text) > (4 << 20)
+    path = tmp_path / "big.obj"
+    path.write_text(text)
+    ref = oracle.load_obj(str(path))
+    for n in ("1", "3", "8", "32"):
+        monkeypatch.setenv("GEL_PARSE_THREADS", n)
+        got = gel_b200.load_obj(str(path))
+        assert all(np.array_equal(bits(a), bits(b)) for a, b in zip(got[:2], ref[:2])), n
+        assert np.array_equal(bits(got[2])[:, [0, 1, 3, 4, 6, 7]], bits(ref[2])[:, [0, 1, 3, 4, 6, 7]]), n
+    bad = tmp_path / "bad.obj"
+    bad.write_text(text + "f 1/1/1 2/2\n")
+    monkeypatch.setenv("GEL_PARSE_THREADS", "4")
+    with pytest.raises(RuntimeError):
+        gel_b200.load_obj(str(bad))
+
+
 def test_bmp_padding_and_topdown(tmp_path):
     import struct
     w, h = 3, 2                                  # row = 9 bytes + 3 pad
