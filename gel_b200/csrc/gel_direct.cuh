@@ -161,9 +161,9 @@ __device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned l
 {
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
-    const int src = id >> 26, x = (id >> 13) & 8191, y = id & 8191;
+    const uint32_t src = id >> 26, x = (id >> 13) & 8191u, y = id & 8191u;
     const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
-    if(key) atomicMax(keys + (size_t) y + (size_t) x * p.yres, key);
+    if(key) atomicMax(keys + (x * (uint32_t) p.yres + y), key);          /* 32-bit unsigned offset inside the view's frame */
 }
 
 template<int PHASE>
@@ -389,7 +389,7 @@ direct_raster_kernel(DirectParams p)
                     const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
                     if(!may_be_inside(nv, nw, eps, den_hi)) continue;
                     const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
-                    if(key) atomicMax(keys + (size_t) y + (size_t) x * p.yres, key);
+                    if(key) atomicMax(keys + ((uint32_t) x * (uint32_t) p.yres + (uint32_t) y), key);
                 }
             }
         }
@@ -447,7 +447,7 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
         atomicOr(p.flags + view, FLAG_TEXCLAMP);           /* the reference reads out of bounds here (R) */
         xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
     }
-    colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+    colour = gel::pshade(__ldg(p.tex + (uint32_t) (xx + yy * p.tw)), shading);
 }
 
 /* D5a: reset (main.c:413-417) of everything outside the view's region -- pure stores.
@@ -499,23 +499,28 @@ direct_resolve_kernel(DirectParams p)
     int rx0, rx1, ry0, ry1;
     if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
     unsigned long long hp = 0, hz = 0;
+    const size_t frame = (size_t) p.xres * p.yres;
+    unsigned long long* vkeys = p.keys + (size_t) view * frame;
+    uint32_t* vpixel = p.pixel + (size_t) view * frame;
+    float* vz = p.zbuf + (size_t) view * frame;
     const int nstrips = (rx1 - rx0 + 8) / 8;
     for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
         const int x = rx0 + strip * 8 + px;
         if(x > rx1) continue;
-        const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
-        unsigned long long next_key = ry0 + py <= ry1 ? p.keys[base + ry0 + py] : CLEAR_KEY;
-        for(int y = ry0 + py; y <= ry1; y += CTA_ROWS)
+        /* per-view bases are CTA-uniform; inside the frame a 32-bit unsigned offset addresses every pixel (<= 2^26) */
+        uint32_t off = (uint32_t) x * (uint32_t) p.yres + (uint32_t) (ry0 + py);
+        unsigned long long next_key = ry0 + py <= ry1 ? vkeys[off] : CLEAR_KEY;
+        for(int y = ry0 + py; y <= ry1; y += CTA_ROWS, off += CTA_ROWS)
         {
             const unsigned long long key = next_key;
-            if(y + CTA_ROWS <= ry1) next_key = p.keys[base + y + CTA_ROWS];   /* one iteration ahead of its use */
+            if(y + CTA_ROWS <= ry1) next_key = vkeys[off + CTA_ROWS];         /* one iteration ahead of its use */
             uint32_t colour; float z;
             direct_shade<COMPACT>(p, view, key, x, y, colour, z);
-            p.keys[base + y] = CLEAR_KEY;                                 /* the buffer is all "no winner" again for the next batch */
-            p.pixel[base + y] = colour;
-            p.zbuf[base + y] = z;
-            if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(colour, idx); hz += gel::salt_mix(__float_as_uint(z), idx); }
+            vkeys[off] = CLEAR_KEY;                                       /* the buffer is all "no winner" again for the next batch */
+            vpixel[off] = colour;
+            vz[off] = z;
+            if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
         }
     }
     if(HASH)
