@@ -40,7 +40,7 @@ constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 #define GEL_FRAG_MAX 256
 #endif
 #ifndef GEL_TWO_PHASE_MIN
-#define GEL_TWO_PHASE_MIN 128
+#define GEL_TWO_PHASE_MIN 8
 #endif
 constexpr int FRAG_MAX = GEL_FRAG_MAX;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
 constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
@@ -392,8 +392,11 @@ __device__ __forceinline__ uint32_t depth_bound_key(float zmax) { return gel::zk
 __device__ __forceinline__ bool survives_hiz(const RasterSmem& sm, uint32_t bbox, uint32_t bound)
 {
     const int gx0 = (bbox & 31) >> 3, gx1 = ((bbox >> 5) & 31) >> 3, gy0 = ((bbox >> 10) & 31) >> 3, gy1 = ((bbox >> 15) & 31) >> 3;
-    if(gx1 - gx0 > 1 || gy1 - gy0 > 1) return true;           /* spans more than 2x2 blocks: not worth testing */
-    const uint32_t lowest = min(min(sm.hiz[gx0 * 4 + gy0], sm.hiz[gx0 * 4 + gy1]), min(sm.hiz[gx1 * 4 + gy0], sm.hiz[gx1 * 4 + gy1]));
+    /* every 8x8 block the bbox touches inside this tile (at most 4 x 4): large pieces are the expensive ones to
+     * rasterise, so they are worth up to 16 shared-memory reads */
+    uint32_t lowest = 0xFFFFFFFFu;
+    for(int gx = gx0; gx <= gx1; gx++)
+        for(int gy = gy0; gy <= gy1; gy++) lowest = min(lowest, sm.hiz[gx * 4 + gy]);
     return !(bound < lowest);
 }
 
