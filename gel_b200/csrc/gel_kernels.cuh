@@ -39,6 +39,9 @@ constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 #ifndef GEL_FRAG_MAX
 #define GEL_FRAG_MAX 256
 #endif
+#ifndef GEL_ZSPLIT_TILE
+#define GEL_ZSPLIT_TILE 0.4f          /* near / far split of a view as a fraction of its depth range: a speed heuristic, any value is exact */
+#endif
 #ifndef GEL_TWO_PHASE_MIN
 #define GEL_TWO_PHASE_MIN 8
 #endif
@@ -560,7 +563,7 @@ raster_kernel(RasterParams p)
         if(tid == 0)
         {
             const float lo = gel::zkey_inv(__ldg(p.vstat + VIEW_STAT_WORDS * view)), hi = gel::zkey_inv(__ldg(p.vstat + VIEW_STAT_WORDS * view + 1));
-            sm.zthr = lo + 0.5f * (hi - lo);
+            sm.zthr = lo + GEL_ZSPLIT_TILE * (hi - lo);
             sm.nfar = 0;
         }
         if(tid < 16) sm.hiz[tid] = 0xFFFFFFFFu;
