@@ -159,15 +159,19 @@ def build_inputs(name: str, workdir: str):
     kind, arg, texn, *_ = WORKLOADS[name]
     obj = os.path.join(workdir, f"{kind}{arg}.obj")
     bmp = os.path.join(workdir, f"tex{texn}.bmp")
+    # several ranks may get here at once: each writes its own temporary and renames it into place (atomic; the content
+    # is deterministic, so whichever rename lands last leaves the same file)
     if not os.path.exists(obj):
         text = synth.sphere_obj_text(arg, arg) if kind == "sphere" else synth.overdraw_obj_text(arg)
-        with open(obj + ".tmp", "w") as f:
+        tmp = f"{obj}.tmp{os.getpid()}"
+        with open(tmp, "w") as f:
             f.write(text)
-        os.replace(obj + ".tmp", obj)
+        os.replace(tmp, obj)
     if not os.path.exists(bmp):
-        with open(bmp + ".tmp", "wb") as f:
+        tmp = f"{bmp}.tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
             f.write(synth.texture_bmp_bytes(texn))
-        os.replace(bmp + ".tmp", bmp)
+        os.replace(tmp, bmp)
     tv, tn, tt = gel_b200.load_obj(obj)
     return {"tv": tv, "tn": tn, "tt": tt, "tex": gel_b200.load_bmp(bmp), "obj": obj, "bmp": bmp}
 

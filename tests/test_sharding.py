@@ -48,3 +48,20 @@ def test_gloo_world2_gather_and_max():
     [p.join(60) for p in ps]
     assert res[0][1] == [k * 7 + 3 for k in range(37)]       # rank 0 holds every view's value, in view order
     assert res[0][2] == res[1][2] == 2.0                     # max over ranks
+
+
+def _build_inputs_worker(args):
+    workdir, name = args
+    import bench
+    d = bench.build_inputs(name, workdir)
+    return int(d["tv"].shape[0]), int(d["tex"].shape[0])
+
+
+def test_ranks_can_generate_the_bench_inputs_concurrently(tmp_path):
+    """Under torchrun every rank calls bench.build_inputs on the same directory at once (a shared temporary name used to
+    make one rank's rename fail): 8 processes, fresh directory, no leftovers."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(8) as pool:
+        out = pool.map(_build_inputs_worker, [(str(tmp_path), "cfg1")] * 8)
+    assert out == [(5000, 256)] * 8
+    assert sorted(os.listdir(tmp_path)) == ["sphere50.obj", "tex256.bmp"]
