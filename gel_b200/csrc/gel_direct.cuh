@@ -29,6 +29,9 @@ namespace gelk {
 #endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
+#ifndef GEL_HIZ_WIDE
+#define GEL_HIZ_WIDE 1
+#endif
 #ifndef GEL_ZSPLIT
 #define GEL_ZSPLIT 0.4f           /* near / far split of a view, as a fraction of its depth range (any value is exact; this one is a speed heuristic) */
 #endif
@@ -48,6 +51,7 @@ constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive tri
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
 constexpr int DIRECT_UNIT_WINDOW = 256;
 constexpr int DIRECT_CAND = 256;                 /* ring of hi-Z survivors waiting for a full batch (phase 1) */
+constexpr int DIRECT_HIZ_SPAN = 4;               /* parked bboxes of up to this many 8x8 blocks per side are tested against the hi-Z map */
 constexpr int DIRECT_TEST_UNROLL = 4;            /* parked records tested per lane per refill round */
 #ifndef GEL_DIRECT_MAX_ROWS
 #define GEL_DIRECT_MAX_ROWS 32
@@ -238,6 +242,14 @@ direct_raster_kernel(DirectParams p)
                     {
                         const uint32_t lowest = min(min(__ldg(hiz + gx0 * p.hby + gy0), __ldg(hiz + gx0 * p.hby + gy1)),
                                                     min(__ldg(hiz + gx1 * p.hby + gy0), __ldg(hiz + gx1 * p.hby + gy1)));
+                        survive[k] = !(rec[k].w < lowest);
+                    }
+                    else if(GEL_HIZ_WIDE && survive[k] && gx1 - gx0 < DIRECT_HIZ_SPAN && gy1 - gy0 < DIRECT_HIZ_SPAN)
+                    {
+                        /* larger bbox: every block it touches (the bigger the triangle, the more a cull saves) */
+                        uint32_t lowest = 0xFFFFFFFFu;
+                        for(int gx = gx0; gx <= gx1; gx++)
+                            for(int gy = gy0; gy <= gy1; gy++) lowest = min(lowest, __ldg(hiz + gx * p.hby + gy));
                         survive[k] = !(rec[k].w < lowest);
                     }
                 }
