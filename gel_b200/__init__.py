@@ -25,7 +25,8 @@ GELCU_E_INVALID, GELCU_E_CUDA, GELCU_E_NOMEM, GELCU_E_NOGPU = -1, -2, -3, -4
 
 # every symbol include/gelcu.h declares (tests check the library exports exactly these)
 GELCU_SYMBOLS = [
-    "gelcu_device_count", "gelcu_create", "gelcu_set_mesh", "gelcu_set_texture", "gelcu_render", "gelcu_render_rgb8",
+    "gelcu_device_count", "gelcu_create", "gelcu_set_mesh", "gelcu_set_mesh_indexed", "gelcu_set_texture", "gelcu_render",
+    "gelcu_render_rgb8", "gelcu_render_region",
     "gelcu_read_frame", "gelcu_set_option", "gelcu_get_stats", "gelcu_debug_transform", "gelcu_debug_bins",
     "gelcu_tile_grid", "gelcu_host_alloc", "gelcu_host_free", "gelcu_destroy", "gelcu_last_error",
 ]
@@ -67,7 +68,9 @@ def cu() -> ctypes.CDLL:
         L.gelcu_device_count.restype = c_int
         L.gelcu_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int]
         L.gelcu_set_mesh.argtypes = [c_void_p, _fp, _fp, _fp, c_int]
+        L.gelcu_set_mesh_indexed.argtypes = [c_void_p, _fp, c_int, _fp, c_int, _fp, c_int, _ip, c_int]
         L.gelcu_set_texture.argtypes = [c_void_p, _u32p, c_int, c_int]
+        L.gelcu_render_region.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, _fp]
         L.gelcu_render.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, _fp]
         L.gelcu_render_rgb8.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, _fp]
         L.gelcu_read_frame.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
@@ -88,6 +91,11 @@ class _Mesh(ctypes.Structure):
     _fields_ = [("tv", _fp), ("tn", _fp), ("tt", _fp), ("ntri", c_int), ("nv", c_int), ("nvt", c_int), ("nvn", c_int)]
 
 
+class _Obj(ctypes.Structure):
+    _fields_ = [("v", _fp), ("vt", _fp), ("vn", _fp), ("faces", _ip), ("nv", c_int), ("nvt", c_int), ("nvn", c_int), ("nfaces", c_int),
+                ("parse_threads", c_int)]
+
+
 class _Tex(ctypes.Structure):
     _fields_ = [("pixels", _u32p), ("w", c_int), ("h", c_int)]
 
@@ -99,6 +107,8 @@ def host() -> ctypes.CDLL:
         L = _load("libgelhost.so")
         L.gel_obj_load.argtypes = [c_char_p, POINTER(_Mesh)]
         L.gel_mesh_free.argtypes = [POINTER(_Mesh)]
+        L.gel_obj_parse.argtypes = [c_char_p, POINTER(_Obj)]
+        L.gel_obj_free.argtypes = [POINTER(_Obj)]
         L.gel_bmp_load.argtypes = [c_char_p, POINTER(_Tex)]
         L.gel_texture_free.argtypes = [POINTER(_Tex)]
         L.gel_view_basis.argtypes = [c_float, c_float, _fp]
@@ -121,6 +131,19 @@ def load_obj(path: str):
     n = m.ntri
     out = tuple(np.ctypeslib.as_array(p, shape=(max(n, 1), 9))[:n].copy() for p in (m.tv, m.tn, m.tt))
     host().gel_mesh_free(byref(m))
+    return out
+
+
+def load_obj_indexed(path: str):
+    """(v (nv, 3), vt (nvt, 3), vn (nvn, 3) float32, faces (nfaces, 9) int32 in the reference's Face layout
+    { va,vb,vc, ta,tb,tc, na,nb,nc }, 0-based) -- gel_obj_parse (reference main.c:129-180), no soup expansion."""
+    o = _Obj()
+    rc = host().gel_obj_parse(path.encode(), byref(o))
+    if rc != 0:
+        raise RuntimeError(f"gel_obj_parse({path}) failed with {rc}")
+    arr = lambda p, n, w, dt: (np.ctypeslib.as_array(p, shape=(n, w)).astype(dt, copy=True) if n else np.zeros((0, w), dt))
+    out = (arr(o.v, o.nv, 3, np.float32), arr(o.vt, o.nvt, 3, np.float32), arr(o.vn, o.nvn, 3, np.float32), arr(o.faces, o.nfaces, 9, np.int32))
+    host().gel_obj_free(byref(o))
     return out
 
 
@@ -204,6 +227,14 @@ class Renderer:
         self.ntri = tv.shape[0]
         _check(cu().gelcu_set_mesh(self._ctx, tv.ctypes.data_as(_fp), tn.ctypes.data_as(_fp), tt.ctypes.data_as(_fp), self.ntri))
 
+    def set_mesh_indexed(self, v, vt, vn, faces):
+        """The indexed OBJ arrays (load_obj_indexed); the soups of main.c:242-286 are generated on the device."""
+        v, vt, vn = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (v, vt, vn))
+        faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 9)
+        self.ntri = faces.shape[0]
+        _check(cu().gelcu_set_mesh_indexed(self._ctx, v.ctypes.data_as(_fp), v.shape[0], vt.ctypes.data_as(_fp), vt.shape[0],
+                                           vn.ctypes.data_as(_fp), vn.shape[0], faces.ctypes.data_as(_ip), faces.shape[0]))
+
     def set_texture(self, xrgb):
         t = np.ascontiguousarray(xrgb, dtype=np.uint32)
         _check(cu().gelcu_set_texture(self._ctx, t.ctypes.data_as(_u32p), t.shape[1], t.shape[0]))
@@ -243,6 +274,20 @@ class Renderer:
                                            h.ctypes.data_as(c_void_p) if h is not None else None, byref(ms)))
         self.last_rc = rc
         return {"rgb": rgb_out, "hash": h, "device_ms": float(ms.value), "rc": rc}
+
+    def render_region(self, bases, pixel_io, rects, *, z_io=None, rgb8=False, hashes=False):
+        """gelcu_render_region: pixel_io (n, xres*yres) uint32 -- or (n, yres, xres, 3) uint8 with rgb8 -- and rects (n, 4)
+        int32 { x0, y0, x1, y1 } are updated in place (dirty-rectangle contract, include/gelcu.h).  Returns dict(hash, device_ms, rc)."""
+        b = np.ascontiguousarray(bases, dtype=np.float32).reshape(-1, 12)
+        n = b.shape[0]
+        assert rects.dtype == np.int32 and rects.shape == (n, 4) and rects.flags.c_contiguous and pixel_io.flags.c_contiguous
+        h = np.zeros((n, 2), dtype=np.uint64) if hashes else None
+        ms = c_float(0.0)
+        rc = _check(cu().gelcu_render_region(self._ctx, b.ctypes.data_as(c_void_p), n, pixel_io.ctypes.data_as(c_void_p),
+                                             z_io.ctypes.data_as(c_void_p) if z_io is not None else None, rects.ctypes.data_as(c_void_p),
+                                             1 if rgb8 else 0, h.ctypes.data_as(c_void_p) if h is not None else None, byref(ms)))
+        self.last_rc = rc
+        return {"hash": h, "device_ms": float(ms.value), "rc": rc}
 
     def read_frame(self, slot: int):
         frame = self.xres * self.yres

@@ -85,13 +85,27 @@ struct DirectScratch               /* per warp */
     float den_hi[32];
 };
 
+/* L2 cache-policy hints (sm_80+ createpolicy; on sm_100a the policy rides in the memory descriptor, no extra
+ * instruction per access).  The fill's 51 MB per frame of write-once stores are marked evict-first and the key buffer's
+ * reductions evict-last, so that the background fill can run UNDER the instruction-bound near pass without pushing the
+ * L2-resident keys out to DRAM (profiles/README.md, round 2). */
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void st_v4_hint(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+}
+template<bool HINT>
+__device__ __forceinline__ void key_max(unsigned long long* ptr, unsigned long long key, uint64_t pol)
+{
+    if(HINT) asm volatile("red.global.max.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(ptr), "l"(key), "l"(pol) : "memory");
+    else atomicMax(ptr, key);
+}
+
 /* screen bbox of a view's vertices, clipped to the frame and widened to whole 8x8 blocks; false when empty */
 __device__ __forceinline__ bool view_region(const DirectParams& p, int view, int& x0, int& x1, int& y0, int& y1)
 {
-    const uint32_t* s = p.vstat + (size_t) view * VSTAT;
-    x0 = max((int) s[2], 0) & ~7; y0 = max((int) s[4], 0) & ~7;
-    x1 = min(min((int) s[3], p.xres - 1) | 7, p.xres - 1); y1 = min(min((int) s[5], p.yres - 1) | 7, p.yres - 1);
-    return x0 <= x1 && y0 <= y1;
+    return region_from_stats(p.vstat + (size_t) view * VSTAT, p.xres, p.yres, x0, x1, y0, y1);
 }
 
 /* the region D0 published for the view; false when empty */
@@ -161,20 +175,22 @@ direct_hiz_kernel(DirectParams p)
 
 /* D1 / D3 ------------------------------------------------------------------------------------------------------- */
 
-__device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned long long* keys, DirectScratch& ws, int i)
+template<bool HINT>
+__device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned long long* keys, DirectScratch& ws, int i, uint64_t pol)
 {
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
     const uint32_t src = id >> 26, x = (id >> 13) & 8191u, y = id & 8191u;
     const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
-    if(key) atomicMax(keys + (x * (uint32_t) p.yres + y), key);          /* 32-bit unsigned offset inside the view's frame */
+    if(key) key_max<HINT>(keys + (x * (uint32_t) p.yres + y), key, pol);  /* 32-bit unsigned offset inside the view's frame */
 }
 
-template<int PHASE>
+template<int PHASE, bool HINT>
 __global__ void __launch_bounds__(DIRECT_THREADS, 1024 / DIRECT_THREADS)
 direct_raster_kernel(DirectParams p)
 {
     __shared__ DirectScratch scratch[DIRECT_WARPS];
+    const uint64_t pol = HINT ? l2_policy_evict_last() : 0ull;
     const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     DirectScratch& ws = scratch[warp];
@@ -363,7 +379,7 @@ direct_raster_kernel(DirectParams p)
                     {
                         __syncwarp();
                         qn -= 32;
-                        direct_resolve(p, keys, ws, qn + lane);
+                        direct_resolve<HINT>(p, keys, ws, qn + lane, pol);
                         __syncwarp();
                     }
                 }
@@ -371,7 +387,7 @@ direct_raster_kernel(DirectParams p)
             __syncwarp();
         }
         __syncwarp();
-        if(lane < qn) direct_resolve(p, keys, ws, lane);
+        if(lane < qn) direct_resolve<HINT>(p, keys, ws, lane, pol);
         qn = 0;
         __syncwarp();
 
@@ -401,7 +417,7 @@ direct_raster_kernel(DirectParams p)
                     const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
                     if(!may_be_inside(nv, nw, eps, den_hi)) continue;
                     const unsigned long long key = fragment_key(nv, nw, q2.w, q3);
-                    if(key) atomicMax(keys + ((uint32_t) x * (uint32_t) p.yres + (uint32_t) y), key);
+                    if(key) key_max<HINT>(keys + ((uint32_t) x * (uint32_t) p.yres + (uint32_t) y), key, pol);
                 }
             }
         }
@@ -494,6 +510,59 @@ direct_fill_kernel(DirectParams p)
         for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
         if((threadIdx.x & 31) == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
     }
+}
+
+/* D5a, overlapped form: the same reset as direct_fill_kernel, as a small persistent grid (a few CTAs per SM) that is
+ * launched BEFORE the near pass on a higher-priority stream and streams its stores out underneath it.  Work item = one
+ * column of one view, view-major like the near pass; 256 threads x 4 rows per store pair.  HINT marks the stores
+ * evict-first in L2. */
+template<bool HASH, bool HINT>
+__global__ void __launch_bounds__(256)
+direct_fill_persistent_kernel(DirectParams p)
+{
+    const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
+    const uint32_t zc = 0xFF7FFFFFu;                                   /* -FLT_MAX */
+    unsigned long long hp = 0, hz = 0;
+    int hview = -1;
+    const int nitems = p.nviews * p.xres;
+    auto flush_hash = [&]() {
+        if constexpr(HASH)
+        {
+            if(hview < 0) return;
+            for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
+            if((threadIdx.x & 31) == 0 && (hp | hz)) { atomicAdd(p.hash + 2 * hview, hp); atomicAdd(p.hash + 2 * hview + 1, hz); }
+            hp = 0; hz = 0;
+        }
+    };
+    for(int item = blockIdx.x; item < nitems; item += gridDim.x)
+    {
+        const int view = item / p.xres, x = item - view * p.xres;
+        if(HASH && view != hview) { flush_hash(); hview = view; }
+        int rx0, rx1, ry0, ry1;
+        const bool region = load_region(p, view, rx0, rx1, ry0, ry1) && x >= rx0 && x <= rx1;
+        const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
+        for(int y4 = threadIdx.x * 4; y4 < p.yres; y4 += 1024)
+        {
+            if(region && y4 >= ry0 && y4 <= ry1) continue;               /* regions are 8-aligned: a group of 4 rows is in or out as a whole */
+            if((p.yres & 3) == 0)
+            {
+                if(HINT) { st_v4_hint(p.pixel + base + y4, 0u, 0u, 0u, 0u, pol); st_v4_hint(p.zbuf + base + y4, zc, zc, zc, zc, pol); }
+                else
+                {
+                    *reinterpret_cast<uint4*>(p.pixel + base + y4) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<float4*>(p.zbuf + base + y4) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                }
+            }
+            for(int k = 0; k < 4; k++)
+            {
+                const int y = y4 + k;
+                if(y >= p.yres || (region && y >= ry0 && y <= ry1)) continue;
+                if((p.yres & 3) != 0) { p.pixel[base + y] = 0u; p.zbuf[base + y] = -FLT_MAX; }
+                if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(0u, idx); hz += gel::salt_mix(zc, idx); }
+            }
+        }
+    }
+    flush_hash();
 }
 
 /* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): a CTA takes strips of 8

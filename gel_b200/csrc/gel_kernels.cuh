@@ -72,6 +72,18 @@ constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f, U_SLACK = 1.00001f;
  * vertices (int min/max of the truncated x and y), 6 parked-triangle counter of the direct pipeline */
 constexpr int VIEW_STAT_WORDS = 8;
 
+/* A view's REGION: the screen bounding box of its transformed vertices (words 2-5), clipped to the frame and widened to
+ * multiples of 8.  Every triangle bbox of main.c:344-347 lies inside it, so everything outside holds reset values.  Host
+ * and device use this one definition (gelcu_render_region reports it; the direct pipeline resolves / fills by it). */
+__host__ __device__ __forceinline__ bool region_from_stats(const uint32_t* s, int xres, int yres, int& x0, int& x1, int& y0, int& y1)
+{
+    const int sx0 = (int) s[2], sx1 = (int) s[3], sy0 = (int) s[4], sy1 = (int) s[5];
+    x0 = (sx0 > 0 ? sx0 : 0) & ~7; y0 = (sy0 > 0 ? sy0 : 0) & ~7;
+    x1 = (sx1 < xres - 1 ? sx1 : xres - 1) | 7; if(x1 > xres - 1) x1 = xres - 1;
+    y1 = (sy1 < yres - 1 ? sy1 : yres - 1) | 7; if(y1 > yres - 1) y1 = yres - 1;
+    return x0 <= x1 && y0 <= y1;
+}
+
 constexpr int XF_PER_THREAD = 4;     /* vertices per thread: amortises the per-warp reductions of the view statistics */
 
 __global__ void __launch_bounds__(256)
@@ -419,6 +431,7 @@ __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, f
     const float u = gel::sub(gel::sub(1.0f, v), w);
     if(!(v >= 0.0f && w >= 0.0f && u >= 0.0f)) return 0ull;
     const float z = gel::add(gel::add(gel::mul(v, q3.y), gel::mul(w, q3.z)), gel::mul(u, q3.x));
+    if(!(z == z)) return 0ull;                          /* a NaN depth never passes `z > zbuff` (main.c:356); its key would be the largest */
     return ((unsigned long long) gel::zkey(z) << 32) | __float_as_uint(q3.w);
 }
 

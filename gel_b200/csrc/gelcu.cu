@@ -9,7 +9,7 @@
  *     K1 -> D0 clear keys -> D1 near triangles -> D2 hi-Z -> D3 parked triangles -> D5 resolve/shade.
  * Frames are double-buffered in HBM so the device->host copy of batch b overlaps the kernels of batch b+1.
  */
-#include "gel_direct.cuh"
+#include "gel_mesh.cuh"
 #include "gel_sink.cuh"
 
 #include <algorithm>
@@ -18,7 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
+#include <cfloat>
 
 using namespace gelk;
 
@@ -39,13 +41,16 @@ int fail(int code, const char* fmt, ...)
 
 template<typename T> void dfree(T*& p) { if(p) cudaFree(p); p = nullptr; }
 
+struct Rect { int x0, y0, x1, y1; bool empty() const { return x1 < x0 || y1 < y0; } };   /* inclusive */
+
 } /* namespace */
 
 struct gelcu_ctx
 {
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;   /* side: HBM-bound fill overlapping the raster kernels */
-    cudaEvent_t side_go = nullptr, side_done = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr, hi_stream = nullptr, aux_stream = nullptr;   /* side / hi: HBM-bound fill beside the raster kernels (hi = higher priority); aux: small result copies */
+    cudaEvent_t side_go = nullptr, side_done = nullptr, stats_go = nullptr, stats_ready[2] = { nullptr, nullptr };
+    int fill_mode = 0, fill_ctas = 1, red_hint = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr; bool trec_compact = false, allow_compact = true;
@@ -62,22 +67,30 @@ struct gelcu_ctx
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
     uint8_t* d_rgb[2] = { nullptr, nullptr };   /* frame sink: upright 24-bit frames, allocated on first use */
     gelcu_view* d_views = nullptr; int views_cap = 0;
-    int* h_cursors = nullptr; uint32_t* h_flags = nullptr; int hcap = 0;
+    int* h_cursors = nullptr; uint32_t* h_flags = nullptr; uint32_t* h_vstat = nullptr; int hcap = 0;
     uint32_t* h_vinit = nullptr;   /* pinned initial per-view statistics (VIEW_STAT_WORDS each) x MAX_BATCH */
     std::vector<cudaEvent_t> ev;   /* EV_PER_BATCH per batch */
     cudaEvent_t render_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
     int last_batch_views = 0, last_buf = 0;
     gelcu_stats stats = {};
+    std::vector<std::pair<int, Rect> > pending_rects, done_rects;   /* region output: (view, rectangle) copied, resets pending / done */
 };
 
 namespace {
 
+void free_bins(gelcu_ctx* c)
+{
+    dfree(c->d_entries); dfree(c->d_descs);
+    c->cap_e = 0; c->cap_d = 0;
+}
+
 void free_work(gelcu_ctx* c)
 {
-    dfree(c->d_xf); dfree(c->d_entries); dfree(c->d_descs); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
+    free_bins(c);
+    dfree(c->d_xf); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]); dfree(c->d_rgb[0]); dfree(c->d_rgb[1]);
-    c->batch = 0; c->cap_e = 0; c->cap_d = 0;
+    c->batch = 0;
 }
 
 #ifndef GEL_RESOLVE_CTAS
@@ -97,42 +110,52 @@ size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
     return b;
 }
 
+/* Work buffers for batches of up to B views.  They are kept between calls: a steady stream of calls with the same (or a
+ * smaller) number of views allocates nothing.  A larger batch or another pipeline rebuilds everything; a bin-pool overflow
+ * (tile pipeline) only replaces the two pools. */
 int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
 {
     const int pipe = active_pipeline(c);
-    if(c->batch >= B && c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_xf && c->work_pipeline == pipe) return GELCU_OK;
-    free_work(c);
-    const size_t frame = (size_t) c->xres * c->yres;
-    CU(cudaMalloc(&c->d_xf, sizeof(float4) * std::max<size_t>(1, (size_t) B * c->nuniq)));
-    CU(cudaMalloc(&c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * B));
-    CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
-    CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
-    CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
-    if(pipe == 2)
+    if(!(c->batch >= B && c->d_xf && c->work_pipeline == pipe))
     {
-        CU(cudaMalloc(&c->d_keys, sizeof(unsigned long long) * B * frame));
-        c->keys_dirty = true;                                   /* filled with "no winner" before the first batch */
-        CU(cudaMalloc(&c->d_hiz, sizeof(uint32_t) * (size_t) B * c->hbx * c->hby));
-        CU(cudaMalloc(&c->d_parked, sizeof(uint4) * std::max<size_t>(1, (size_t) B * c->ntri)));
-        CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP + DIRECT_WARPS + 1)));
-        CU(cudaMalloc(&c->d_region, sizeof(int) * REGION_WORDS * B));
+        free_work(c);
+        const size_t frame = (size_t) c->xres * c->yres;
+        CU(cudaMalloc(&c->d_xf, sizeof(float4) * std::max<size_t>(1, (size_t) B * c->nuniq)));
+        CU(cudaMalloc(&c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * B));
+        CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
+        CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
+        CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
+        if(pipe == 2)
+        {
+            CU(cudaMalloc(&c->d_keys, sizeof(unsigned long long) * B * frame));
+            c->keys_dirty = true;                                   /* filled with "no winner" before the first batch */
+            CU(cudaMalloc(&c->d_hiz, sizeof(uint32_t) * (size_t) B * c->hbx * c->hby));
+            CU(cudaMalloc(&c->d_parked, sizeof(uint4) * std::max<size_t>(1, (size_t) B * c->ntri)));
+            CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP + DIRECT_WARPS + 1)));
+            CU(cudaMalloc(&c->d_region, sizeof(int) * REGION_WORDS * B));
+        }
+        else
+        {
+            CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
+            CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
+            CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
+            CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
+            CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+        }
+        for(int k = 0; k < 2; k++)
+        {
+            CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
+            CU(cudaMalloc(&c->d_z[k], sizeof(float) * B * frame));
+        }
+        c->batch = B; c->work_pipeline = pipe;
     }
-    else
+    if(pipe != 2 && !(c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_entries))
     {
-        CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) B * cap_e)));
-        CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) B * cap_d)));
-        CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
-        CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
-        CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
-        CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
-        CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+        free_bins(c);
+        CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) c->batch * cap_e)));
+        CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) c->batch * cap_d)));
+        c->cap_e = cap_e; c->cap_d = cap_d;
     }
-    for(int k = 0; k < 2; k++)
-    {
-        CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
-        CU(cudaMalloc(&c->d_z[k], sizeof(float) * B * frame));
-    }
-    c->batch = B; c->cap_e = cap_e; c->cap_d = cap_d; c->work_pipeline = pipe;
     return GELCU_OK;
 }
 
@@ -144,7 +167,7 @@ int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 }
 
 /* Enqueues the kernels for `n` views starting at d_views + first into frame buffer `buf`. */
-int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool want_rgb, cudaEvent_t* ev)
+int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool want_rgb, bool want_stats, cudaEvent_t* ev)
 {
     cudaStream_t s = c->stream;
     const int pipe = c->work_pipeline;
@@ -165,6 +188,16 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         c->stats.kernels_launched++;
     }
     CU(cudaEventRecord(ev[1], s));
+    if(want_stats)
+    {
+        /* region output: the per-view vertex statistics (complete after K1) go to the host on their own stream while
+         * the raster kernels run; the host turns them into the rectangles it copies (region_from_stats) */
+        CU(cudaEventRecord(c->stats_go, s));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->stats_go, 0));
+        CU(cudaMemcpyAsync(c->h_vstat + (size_t) VIEW_STAT_WORDS * first, c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * n, cudaMemcpyDeviceToHost, c->aux_stream));
+        CU(cudaEventRecord(c->stats_ready[buf], c->aux_stream));
+        c->stats.d2h_bytes += sizeof(uint32_t) * VIEW_STAT_WORDS * (size_t) n;
+    }
     if(pipe == 2)
     {
         DirectParams dp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_trec, c->d_tex, c->tw, c->th, c->d_keys, c->d_hiz, c->d_parked, c->d_far_count, c->d_region, c->d_vstat,
@@ -175,32 +208,54 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         c->stats.kernels_launched++;
         CU(cudaEventRecord(ev[2], s));
         CU(cudaEventRecord(c->side_go, s));                              /* the region is known from here on */
+        /* Reset (main.c:413-417) of everything outside the view's region: pure stores, beside the raster kernels.
+         *   fill_mode 0: a plain grid on the side stream, submitted AFTER the near pass -- it fills in as the near pass
+         *                drains and runs beside the hi-Z / parked / resolve kernels;
+         *   fill_mode 1: a few persistent CTAs per SM on a HIGHER-PRIORITY stream, submitted BEFORE the near pass, with
+         *                evict-first stores: the 51 MB per cfg-3 frame stream out underneath the issue-bound near pass
+         *                (which uses a fifth of the DRAM bandwidth) without evicting the L2-resident key buffer;
+         *   fill_mode 2: mode 1 without the cache hint (the control of that experiment). */
+        const bool early_fill = c->fill_mode != 0;
+        cudaStream_t fs = early_fill ? c->hi_stream : c->side_stream;
+        auto launch_fill = [&]() -> int {
+            CU(cudaStreamWaitEvent(fs, c->side_go, 0));
+            if(early_fill)
+            {
+                const int grid = c->num_sms * std::max(1, std::min(c->fill_ctas, 8));
+                if(c->fill_mode == 1) { if(want_hash) direct_fill_persistent_kernel<true, true><<<grid, 256, 0, fs>>>(dp); else direct_fill_persistent_kernel<false, true><<<grid, 256, 0, fs>>>(dp); }
+                else { if(want_hash) direct_fill_persistent_kernel<true, false><<<grid, 256, 0, fs>>>(dp); else direct_fill_persistent_kernel<false, false><<<grid, 256, 0, fs>>>(dp); }
+            }
+            else
+            {
+                const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
+                if(want_hash) direct_fill_kernel<true><<<fgrid, 256, 0, fs>>>(dp);
+                else direct_fill_kernel<false><<<fgrid, 256, 0, fs>>>(dp);
+            }
+            CU(cudaEventRecord(c->side_done, fs));
+            c->stats.kernels_launched++;
+            return GELCU_OK;
+        };
+        if(early_fill) { const int rc = launch_fill(); if(rc) return rc; }
         if(c->ntri > 0)
         {
-            direct_raster_kernel<0><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            if(c->red_hint) direct_raster_kernel<0, true><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            else direct_raster_kernel<0, false><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched++;
         }
         CU(cudaEventRecord(ev[3], s));
-        /* everything outside the view's region is reset by pure stores on the side stream, submitted AFTER the near
-         * pass: D1 (one warp per CTA, 56 registers) leaves room for one fill CTA per SM, so this HBM traffic runs
-         * underneath the instruction-bound raster kernels */
-        CU(cudaStreamWaitEvent(c->side_stream, c->side_go, 0));
-        const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
-        if(want_hash) direct_fill_kernel<true><<<fgrid, 256, 0, c->side_stream>>>(dp);
-        else direct_fill_kernel<false><<<fgrid, 256, 0, c->side_stream>>>(dp);
-        CU(cudaEventRecord(c->side_done, c->side_stream));
-        c->stats.kernels_launched++;
+        if(!early_fill) { const int rc = launch_fill(); if(rc) return rc; }
         if(c->ntri > 0)
         {
             direct_hiz_kernel<<<dim3(32, n), 256, 0, s>>>(dp);
-            direct_raster_kernel<1><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            if(c->red_hint) direct_raster_kernel<1, true><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
+            else direct_raster_kernel<1, false><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched += 2;
         }
         const dim3 sgrid(std::min(RESOLVE_CTAS, (c->xres + 7) / 8), n);   /* one strip of 8 columns per CTA when the grid allows; CTAs past the region's last strip exit at once */
         if(c->trec_compact) { if(want_hash) direct_resolve_kernel<true, true><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, true><<<sgrid, 256, 0, s>>>(dp); }
         else { if(want_hash) direct_resolve_kernel<true, false><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, false><<<sgrid, 256, 0, s>>>(dp); }
         c->stats.kernels_launched++;
-        CU(cudaStreamWaitEvent(s, c->side_done, 0));
+        CU(cudaStreamWaitEvent(s, c->side_done, 0));                    /* the batch ends when its frames are complete: resolve AND fill */
     }
     else
     {
@@ -247,11 +302,24 @@ int ensure_host(gelcu_ctx* c, int n)
     if(c->hcap >= n) return GELCU_OK;
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
-    c->h_cursors = nullptr; c->h_flags = nullptr; c->hcap = 0;
+    if(c->h_vstat) cudaFreeHost(c->h_vstat);
+    c->h_cursors = nullptr; c->h_flags = nullptr; c->h_vstat = nullptr; c->hcap = 0;
     CU(cudaMallocHost(&c->h_cursors, sizeof(int) * 4 * n));
     CU(cudaMallocHost(&c->h_flags, sizeof(uint32_t) * n));
+    CU(cudaMallocHost(&c->h_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * n));
     c->hcap = n;
     return GELCU_OK;
+}
+
+/* Pipeline choice: mean projected triangle area (model units -> pixels at depth 0: yres/2 px per unit, main.c:290,
+ * 302-314).  Tiny triangles -> direct pipeline; otherwise the tile pipeline. */
+int choose_pipeline(int ntri, double mean_tri_px) { return (ntri >= 65536 && mean_tri_px < 32.0) ? 2 : 1; }
+
+void drop_mesh(gelcu_ctx* c)
+{
+    c->have_mesh = false; c->ntri = 0; c->nuniq = 0;
+    free_work(c);
+    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
 }
 
 int check_ready(gelcu_ctx* c)
@@ -303,12 +371,18 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     cudaError_t s1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t s2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+    if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    if(s2 == cudaSuccess) s2 = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if(s2 == cudaSuccess) s2 = cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, prio_greatest);
     if(s1 == cudaSuccess) s1 = cudaEventCreateWithFlags(&c->side_go, cudaEventDisableTiming);
     if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
+    if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->stats_go, cudaEventDisableTiming);
     for(int k = 0; k < 2 && s1 == cudaSuccess && s2 == cudaSuccess; k++)
     {
         s1 = cudaEventCreateWithFlags(&c->render_done[k], cudaEventDisableTiming);
         s2 = cudaEventCreateWithFlags(&c->copy_done[k], cudaEventDisableTiming);
+        if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->stats_ready[k], cudaEventDisableTiming);
     }
     if(s1 != cudaSuccess || s2 != cudaSuccess) { delete c; return fail(GELCU_E_CUDA, "stream/event creation failed"); }
     if(cudaMallocHost(&c->h_vinit, sizeof(uint32_t) * VIEW_STAT_WORDS * MAX_BATCH) != cudaSuccess) { delete c; return fail(GELCU_E_NOMEM, "pinned allocation failed"); }
@@ -373,8 +447,6 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         }
         idx[cidx % 3][cidx / 3] = found;
     }
-    /* Pipeline choice: mean projected triangle area (model units -> pixels at depth 0: yres/2 px per unit, main.c:290,
-     * 302-314).  Tiny triangles -> direct pipeline; otherwise the tile pipeline. */
     double area = 0.0;
     for(int t = 0; t < ntri; t++)
     {
@@ -384,8 +456,7 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         const double a2 = cx * cx + cy * cy + cz * cz;
         if(a2 == a2 && a2 < 1e30) area += 0.5 * sqrt(a2);
     }
-    c->mean_tri_px = ntri > 0 ? area / ntri * (0.5 * c->yres) * (0.5 * c->yres) : 0.0;
-    c->pipeline_auto = (ntri >= 65536 && c->mean_tri_px < 32.0) ? 2 : 1;
+    const double mean_px = ntri > 0 ? area / ntri * (0.5 * c->yres) * (0.5 * c->yres) : 0.0;
     std::vector<float2> uv(ncorner);
     for(size_t cidx = 0; cidx < ncorner; cidx++) uv[cidx] = make_float2(tt[3 * cidx], tt[3 * cidx + 1]);   /* tt.z is never read, main.c:360-361 */
 
@@ -412,15 +483,13 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         }
     }
 
-    free_work(c);
-    dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
-    c->ntri = ntri; c->nuniq = (int) vpos.size(); c->have_mesh = true;
+    /* the context has no mesh until the last upload has succeeded (a failed allocation must not leave half a mesh) */
+    drop_mesh(c);
     const size_t nu = std::max<size_t>(1, vpos.size()), nt = std::max<size_t>(1, (size_t) ntri);
     CU(cudaMalloc(&c->d_vpos, sizeof(float4) * nu)); CU(cudaMalloc(&c->d_vnrm, sizeof(float4) * nu));
     CU(cudaMalloc(&c->d_i0, 4 * nt)); CU(cudaMalloc(&c->d_i1, 4 * nt)); CU(cudaMalloc(&c->d_i2, 4 * nt));
     CU(cudaMalloc(&c->d_uv, sizeof(float2) * 3 * nt));
     CU(cudaMalloc(&c->d_trec, sizeof(uint4) * std::max<size_t>(1, trec.size())));
-    c->trec_compact = compact;
     if(ntri > 0)
     {
         CU(cudaMemcpy(c->d_vpos, vpos.data(), sizeof(float4) * vpos.size(), cudaMemcpyHostToDevice));
@@ -431,6 +500,76 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
         CU(cudaMemcpy(c->d_uv, uv.data(), sizeof(float2) * uv.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_trec, trec.data(), sizeof(uint4) * trec.size(), cudaMemcpyHostToDevice));
     }
+    c->mean_tri_px = mean_px; c->pipeline_auto = choose_pipeline(ntri, mean_px);
+    c->trec_compact = compact;
+    c->ntri = ntri; c->nuniq = (int) vpos.size(); c->have_mesh = true;
+    return GELCU_OK;
+}
+
+int gelcu_set_mesh_indexed(gelcu_ctx* c, const float* v, int nv, const float* vt, int nvt, const float* vn, int nvn, const int* faces, int nfaces)
+{
+    if(!c) return fail(GELCU_E_INVALID, "null context");
+    if(nv < 0 || nvt < 0 || nvn < 0 || nfaces < 0 || (nfaces > 0 && (!v || !vt || !vn || !faces || nv == 0 || nvt == 0 || nvn == 0)))
+        return fail(GELCU_E_INVALID, "bad indexed mesh arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    drop_mesh(c);
+    /* staging: the OBJ arrays as they are (36 bytes per face + the vertex lines, against 108 bytes per face of soups) */
+    struct Staging
+    {
+        float *v = nullptr, *vt = nullptr, *vn = nullptr; int* faces = nullptr; unsigned long long* keys = nullptr; uint32_t *ranks = nullptr, *count = nullptr, *result = nullptr; double* area = nullptr;
+        ~Staging() { cudaFree(v); cudaFree(vt); cudaFree(vn); cudaFree(faces); cudaFree(keys); cudaFree(ranks); cudaFree(count); cudaFree(result); cudaFree(area); }
+    } st;
+    const size_t ncorner = (size_t) nfaces * 3;
+    size_t tsize = 1024; while(tsize < ncorner * 2) tsize <<= 1;
+    CU(cudaMalloc(&st.v, sizeof(float) * 3 * std::max(1, nv))); CU(cudaMalloc(&st.vt, sizeof(float) * 3 * std::max(1, nvt))); CU(cudaMalloc(&st.vn, sizeof(float) * 3 * std::max(1, nvn)));
+    CU(cudaMalloc(&st.faces, sizeof(int) * 9 * std::max<size_t>(1, (size_t) nfaces)));
+    CU(cudaMalloc(&st.keys, sizeof(unsigned long long) * tsize)); CU(cudaMalloc(&st.ranks, sizeof(uint32_t) * tsize));
+    CU(cudaMalloc(&st.count, sizeof(uint32_t) * std::max(1, nv))); CU(cudaMalloc(&st.result, sizeof(uint32_t) * 4)); CU(cudaMalloc(&st.area, sizeof(double)));
+    cudaStream_t s = c->stream;
+    if(nv) CU(cudaMemcpyAsync(st.v, v, sizeof(float) * 3 * (size_t) nv, cudaMemcpyHostToDevice, s));
+    if(nvt) CU(cudaMemcpyAsync(st.vt, vt, sizeof(float) * 3 * (size_t) nvt, cudaMemcpyHostToDevice, s));
+    if(nvn) CU(cudaMemcpyAsync(st.vn, vn, sizeof(float) * 3 * (size_t) nvn, cudaMemcpyHostToDevice, s));
+    if(nfaces) CU(cudaMemcpyAsync(st.faces, faces, sizeof(int) * 9 * (size_t) nfaces, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(st.keys, 0xFF, sizeof(unsigned long long) * tsize, s));
+    CU(cudaMemsetAsync(st.count, 0, sizeof(uint32_t) * std::max(1, nv), s));
+    CU(cudaMemsetAsync(st.result, 0, sizeof(uint32_t) * 4, s));
+    CU(cudaMemsetAsync(st.area, 0, sizeof(double), s));
+    MeshBuild mb = { st.v, st.vt, st.vn, st.faces, nv, nvt, nvn, nfaces, st.keys, st.ranks, (uint32_t) (tsize - 1), st.count, st.result, st.area };
+    const int grid = c->num_sms * 8;
+    if(nv) mesh_maxlen_kernel<<<grid, 256, 0, s>>>(mb);
+    if(nfaces) mesh_pairs_kernel<<<grid, 256, 0, s>>>(mb);
+    mesh_scan_kernel<<<1, 1024, 0, s>>>(mb);
+    uint32_t result[4] = { 0, 0, 0, 0 };
+    CU(cudaMemcpyAsync(result, st.result, sizeof result, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    if(result[1] & MESH_BAD_INDEX) return fail(GELCU_E_INVALID, "a face index lies outside its v / vt / vn array (the reference reads out of bounds there, main.c:248-250)");
+    float maxlen; memcpy(&maxlen, &result[0], 4);
+    /* tvgen: `const int scale = vmaxlen(obj.vsv)` then `1.0f / scale` (main.c:244,253) */
+    if(nfaces > 0 && !(maxlen >= 1.0f && maxlen < 2147483648.0f)) return fail(GELCU_E_INVALID, "max |v| = %g: the reference's scale 1.0f / (int) max|v| is undefined (main.c:244,253)", (double) maxlen);
+    const int scale = nfaces > 0 ? (int) maxlen : 1;
+    const float inv = 1.0f / (float) scale;
+    const int nuniq = (int) result[2];
+    const bool compact = c->allow_compact && (size_t) nuniq < ((size_t) 1 << TREC_COMPACT_BITS);
+    const size_t nu = std::max<size_t>(1, (size_t) nuniq), nt = std::max<size_t>(1, (size_t) nfaces);
+    CU(cudaMalloc(&c->d_vpos, sizeof(float4) * nu)); CU(cudaMalloc(&c->d_vnrm, sizeof(float4) * nu));
+    CU(cudaMalloc(&c->d_i0, 4 * nt)); CU(cudaMalloc(&c->d_i1, 4 * nt)); CU(cudaMalloc(&c->d_i2, 4 * nt));
+    CU(cudaMalloc(&c->d_uv, sizeof(float2) * 3 * nt));
+    CU(cudaMalloc(&c->d_trec, sizeof(uint4) * (size_t) (compact ? 2 : TREC_QUADS) * nt));
+    double area = 0.0;
+    if(nfaces)
+    {
+        MeshOut mo = { c->d_vpos, c->d_vnrm, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_trec, compact ? 1 : 0, inv };
+        mesh_emit_kernel<<<grid, 256, 0, s>>>(mb, mo);
+        CU(cudaMemcpyAsync(&area, st.area, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        CU(cudaGetLastError());
+    }
+    const double mean_px = nfaces > 0 ? area / nfaces * (0.5 * c->yres) * (0.5 * c->yres) : 0.0;
+    c->mean_tri_px = mean_px; c->pipeline_auto = choose_pipeline(nfaces, mean_px);
+    c->trec_compact = compact;
+    c->ntri = nfaces; c->nuniq = nuniq; c->have_mesh = true;
     return GELCU_OK;
 }
 
@@ -454,6 +593,9 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
+    else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_mode must be 0, 1 or 2"); c->fill_mode = value; }
+    else if(!strcmp(name, "fill_ctas_per_sm")) { if(value < 1 || value > 8) return fail(GELCU_E_INVALID, "fill_ctas_per_sm out of [1,8]"); c->fill_ctas = value; }
+    else if(!strcmp(name, "red_hint")) c->red_hint = value != 0;
     else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
     return GELCU_OK;
@@ -468,8 +610,52 @@ int gelcu_get_stats(gelcu_ctx* c, gelcu_stats* out)
 
 namespace {
 
+/* ---- host side of the region output (gelcu_render_region) ---- */
+
+Rect clip_rect(const gelcu_rect& r, int xres, int yres)
+{
+    Rect o = { std::max(r.x0, 0), std::max(r.y0, 0), std::min(r.x1, xres - 1), std::min(r.y1, yres - 1) };
+    return o;
+}
+
+/* reset values (main.c:413-417) into rows [ya, yb] of columns [xa, xb] of a sideways frame */
+void host_reset_sideways(uint32_t* pixel, float* z, int yres, int xa, int xb, int ya, int yb)
+{
+    if(xa > xb || ya > yb) return;
+    for(int x = xa; x <= xb; x++)
+    {
+        const size_t base = (size_t) x * yres + ya;
+        if(pixel) memset(pixel + base, 0, sizeof(uint32_t) * (size_t) (yb - ya + 1));
+        if(z) std::fill(z + base, z + base + (yb - ya + 1), -FLT_MAX);
+    }
+}
+
+/* zeros into columns [xa, xb] of the upright rows that hold screen rows [ya, yb] (row wy = yres - 1 - y) */
+void host_reset_upright(uint8_t* rgb, int xres, int yres, int xa, int xb, int ya, int yb)
+{
+    if(xa > xb || ya > yb) return;
+    for(int y = ya; y <= yb; y++)
+        memset(rgb + ((size_t) (yres - 1 - y) * xres + xa) * 3, 0, 3 * (size_t) (xb - xa + 1));
+}
+
+/* the part of `old` that `now` does not cover goes back to reset values (at most four strips) */
+void host_reset_stale(void* pixel, float* z, bool rgb8, int xres, int yres, const Rect& old, const Rect& now)
+{
+    if(old.empty()) return;
+    auto strip = [&](int xa, int xb, int ya, int yb) {
+        if(rgb8) host_reset_upright((uint8_t*) pixel, xres, yres, xa, xb, ya, yb);
+        else host_reset_sideways((uint32_t*) pixel, z, yres, xa, xb, ya, yb);
+    };
+    if(now.empty()) { strip(old.x0, old.x1, old.y0, old.y1); return; }
+    strip(old.x0, std::min(old.x1, now.x0 - 1), old.y0, old.y1);                         /* columns left of the new rectangle  */
+    strip(std::max(old.x0, now.x1 + 1), old.x1, old.y0, old.y1);                         /* columns right of it                */
+    const int xa = std::max(old.x0, now.x0), xb = std::min(old.x1, now.x1);              /* shared columns: rows below / above */
+    strip(xa, xb, old.y0, std::min(old.y1, now.y0 - 1));
+    strip(xa, xb, std::max(old.y0, now.y1 + 1), old.y1);
+}
+
 int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
-                uint32_t* pixel_out, float* z_out, uint8_t* rgb_out, uint64_t* hash_out, float* device_ms)
+                uint32_t* pixel_out, float* z_out, uint8_t* rgb_out, gelcu_rect* rect_io, uint64_t* hash_out, float* device_ms)
 {
     int rc = check_ready(c);
     if(rc) return rc;
@@ -487,10 +673,12 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
     }
     rc = ensure_host(c, nviews); if(rc) return rc;
     const int nchunks = (c->ntri + BIN_CHUNK - 1) / BIN_CHUNK;
-    int cap_e = c->cap_e > 0 ? c->cap_e : (int) std::min<size_t>((size_t) 1 << 30, (size_t) 2 * c->ntri + 4096);
+    int cap_e = c->cap_e > 0 ? c->cap_e : (int) std::min<size_t>((size_t) 1 << 30, (size_t) 4 * c->ntri + 4096);
     int cap_d = c->cap_d > 0 ? c->cap_d : (int) std::min<size_t>((size_t) 1 << 30, (size_t) 32 * nchunks + 4096);
+    const bool want_frames = pixel_out || z_out || rgb_out;
+    const bool want_region = rect_io != nullptr;
 
-    for(int attempt = 0; attempt < 4; attempt++)
+    for(int attempt = 0; attempt < 6; attempt++)
     {
         const int B = std::min(nviews, std::max(c->batch, default_batch(c, cap_e, cap_d)));
         rc = ensure_work(c, B, cap_e, cap_d); if(rc) return rc;
@@ -498,8 +686,8 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
             for(int k = 0; k < 2; k++) CU(cudaMalloc(&c->d_rgb[k], 3 * frame * (size_t) c->batch));
         /* frames that go back to the host: a call is cut into at least four batches so that the copy of one batch
          * runs under the rendering of the next (the copy is the longer of the two by an order of magnitude) */
-        int bsz = c->batch;
-        if((pixel_out || z_out || rgb_out) && c->batch_opt == 0) bsz = std::min(c->batch, std::max(8, (nviews + 3) / 4));
+        int bsz = std::min(c->batch, nviews);
+        if(want_frames && c->batch_opt == 0) bsz = std::min(c->batch, std::max(8, (nviews + 3) / 4));
         const int nb = (nviews + bsz - 1) / bsz;
         rc = ensure_events(c, nb); if(rc) return rc;
         c->stats.kernels_launched = 0; c->stats.h2d_bytes = 0; c->stats.d2h_bytes = 0; c->stats.batches = nb; c->stats.views = nviews;
@@ -518,30 +706,77 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         auto issue_copies = [&](int b) -> int {
             const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
             CU(cudaStreamWaitEvent(c->copy_stream, c->render_done[buf], 0));
-            if(pixel_out) { CU(cudaMemcpyAsync(pixel_out + frame * first, c->d_pixel[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
-            if(z_out) { CU(cudaMemcpyAsync(z_out + frame * first, c->d_z[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
-            if(rgb_out) { CU(cudaMemcpyAsync(rgb_out + 3 * frame * first, c->d_rgb[buf], 3 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 3 * frame * n; }
+            if(want_region)
+            {
+                /* only each view's region crosses PCIe (a strided copy per frame); the strips of the caller's frame that
+                 * the previous occupant lit and this view does not are reset here, on the host, while the copies run */
+                CU(cudaEventSynchronize(c->stats_ready[buf]));
+                for(int v = 0; v < n; v++)
+                {
+                    Rect now;
+                    if(!region_from_stats(c->h_vstat + (size_t) VIEW_STAT_WORDS * (first + v), c->xres, c->yres, now.x0, now.x1, now.y0, now.y1)) now = Rect{ 0, 0, -1, -1 };
+                    if(!now.empty())
+                    {
+                        const size_t w = (size_t) (now.x1 - now.x0 + 1), h = (size_t) (now.y1 - now.y0 + 1);
+                        if(rgb_out)
+                        {
+                            const size_t off = ((size_t) (c->yres - 1 - now.y1) * c->xres + now.x0) * 3, pitch = (size_t) c->xres * 3;
+                            CU(cudaMemcpy2DAsync(rgb_out + 3 * frame * (first + v) + off, pitch, c->d_rgb[buf] + 3 * frame * v + off, pitch, 3 * w, h, cudaMemcpyDeviceToHost, c->copy_stream));
+                            c->stats.d2h_bytes += 3 * w * h;
+                        }
+                        else
+                        {
+                            const size_t off = (size_t) now.x0 * c->yres + now.y0, pitch = (size_t) c->yres * 4;
+                            if(pixel_out) { CU(cudaMemcpy2DAsync(pixel_out + frame * (first + v) + off, pitch, c->d_pixel[buf] + frame * v + off, pitch, 4 * h, w, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * w * h; }
+                            if(z_out) { CU(cudaMemcpy2DAsync(z_out + frame * (first + v) + off, pitch, c->d_z[buf] + frame * v + off, pitch, 4 * h, w, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * w * h; }
+                        }
+                    }
+                    c->pending_rects.push_back(std::make_pair(first + v, now));
+                }
+            }
+            else
+            {
+                if(pixel_out) { CU(cudaMemcpyAsync(pixel_out + frame * first, c->d_pixel[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
+                if(z_out) { CU(cudaMemcpyAsync(z_out + frame * first, c->d_z[buf], 4 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 4 * frame * n; }
+                if(rgb_out) { CU(cudaMemcpyAsync(rgb_out + 3 * frame * first, c->d_rgb[buf], 3 * frame * n, cudaMemcpyDeviceToHost, c->copy_stream)); c->stats.d2h_bytes += 3 * frame * n; }
+            }
             CU(cudaEventRecord(c->copy_done[buf], c->copy_stream));
             return GELCU_OK;
         };
+        /* host-side resets for the views whose copies have been issued (they touch only pixels outside the new rectangles) */
+        auto reset_stale = [&]() {
+            for(const auto& pr : c->pending_rects)
+            {
+                const int k = pr.first;
+                const Rect old = clip_rect(rect_io[k], c->xres, c->yres);
+                host_reset_stale(rgb_out ? (void*) (rgb_out + 3 * frame * k) : (void*) (pixel_out ? pixel_out + frame * k : nullptr),
+                                 z_out ? z_out + frame * k : nullptr, rgb_out != nullptr, c->xres, c->yres, old, pr.second);
+            }
+            c->done_rects.insert(c->done_rects.end(), c->pending_rects.begin(), c->pending_rects.end());
+            c->pending_rects.clear();
+        };
+        c->pending_rects.clear(); c->done_rects.clear();
 
         for(int b = 0; b < nb; b++)
         {
             const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
-            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, rgb_out != nullptr, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
+            if(want_region && b >= 1) CU(cudaStreamWaitEvent(c->stream, c->stats_ready[(b - 1) & 1], 0));   /* d_vstat is reused */
+            rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, rgb_out != nullptr, want_region, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
             /* small per-batch results ride the render stream (the next batch overwrites their device copies) */
             CU(cudaMemcpyAsync(c->h_cursors + 4 * first, c->d_cursors, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaMemcpyAsync(c->h_flags + first, c->d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
             if(hash_out) { CU(cudaMemcpyAsync(hash_out + 2 * (size_t) first, c->d_hash, 16 * (size_t) n, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2h_bytes += 16 * (size_t) n; }
             CU(cudaEventRecord(c->render_done[buf], c->stream));
-            if(b >= 1 && (pixel_out || z_out || rgb_out)) { rc = issue_copies(b - 1); if(rc) return rc; }
+            if(b >= 1 && want_frames) { rc = issue_copies(b - 1); if(rc) return rc; if(want_region) reset_stale(); }
             c->last_batch_views = n; c->last_buf = buf;
         }
-        if(pixel_out || z_out || rgb_out) { rc = issue_copies(nb - 1); if(rc) return rc; }
+        if(want_frames) { rc = issue_copies(nb - 1); if(rc) return rc; if(want_region) reset_stale(); }
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->side_stream));
+        CU(cudaStreamSynchronize(c->hi_stream));
+        CU(cudaStreamSynchronize(c->aux_stream));
         c->keys_dirty = false;
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
@@ -553,28 +788,37 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         }
         if(flags & FLAG_OVERFLOW)
         {
-            /* an entry or segment pool ran out: grow both to the measured need and render the call again */
-            cap_e = (int) std::min<size_t>((size_t) 1 << 30, std::max<size_t>(cap_e, (size_t) need_e + need_e / 8 + 1024));
-            cap_d = (int) std::min<size_t>((size_t) 1 << 30, std::max<size_t>(cap_d, (size_t) need_d + need_d / 8 + 1024));
-            if(per_view_bytes(c, cap_e, cap_d) > ((size_t) 150 << 30))
+            /* an entry or segment pool ran out: both grow geometrically past the measured need (so a slowly changing view
+             * does not overflow again a few frames later), only the pools are reallocated, and the call is rendered again.
+             * The frames already copied are overwritten by the second pass; their rectangles are the same. */
+            cap_e = (int) std::min<size_t>((size_t) 1 << 30, std::max<size_t>((size_t) 2 * cap_e, (size_t) need_e + need_e / 2 + 1024));
+            cap_d = (int) std::min<size_t>((size_t) 1 << 30, std::max<size_t>((size_t) 2 * cap_d, (size_t) need_d + need_d / 2 + 1024));
+            if(per_view_bytes(c, cap_e, cap_d) * (size_t) c->batch > ((size_t) 150 << 30))
                 return fail(GELCU_E_NOMEM, "bin lists need %d entries / %d segments per view, beyond device memory", need_e, need_d);
-            const int keep = c->batch_opt;
-            free_work(c);
-            c->batch_opt = keep;
             continue;
         }
-        float ms = 0.0f, t = 0.0f;
-        CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[EV_PER_BATCH * (nb - 1) + 4]));
-        c->stats.ms_total = ms;
-        if(c->stage_timing)
-            for(int b = 0; b < nb; b++)
+        if(want_region)
+            for(const auto& pr : c->done_rects)
             {
-                cudaEvent_t* e = &c->ev[EV_PER_BATCH * b];
+                gelcu_rect& r = rect_io[pr.first];
+                r.x0 = pr.second.x0; r.y0 = pr.second.y0; r.x1 = pr.second.x1; r.y1 = pr.second.y1;
+            }
+        /* device time = the batches' own spans (first kernel start to frames complete), summed: stalls of the render stream
+         * between batches -- waiting for a frame buffer whose copy is still running -- are not kernel time */
+        float ms = 0.0f, t = 0.0f;
+        for(int b = 0; b < nb; b++)
+        {
+            cudaEvent_t* e = &c->ev[EV_PER_BATCH * b];
+            CU(cudaEventElapsedTime(&t, e[0], e[4])); ms += t;
+            if(c->stage_timing)
+            {
                 CU(cudaEventElapsedTime(&t, e[0], e[1])); c->stats.ms_transform += t;
                 CU(cudaEventElapsedTime(&t, e[1], e[2])); c->stats.ms_bin += t;
                 CU(cudaEventElapsedTime(&t, e[2], e[4])); c->stats.ms_raster += t;
                 CU(cudaEventElapsedTime(&t, e[2], e[3])); c->stats.ms_dominant += t;
             }
+        }
+        c->stats.ms_total = ms;
         if(device_ms) *device_ms = ms;
         c->stats.bin_entries = entries;
         c->stats.pipeline = (uint32_t) c->work_pipeline;
@@ -590,13 +834,22 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
 int gelcu_render(gelcu_ctx* c, const gelcu_view* views, int nviews,
                  uint32_t* pixel_out, float* z_out, uint64_t* hash_out, float* device_ms)
 {
-    return render_impl(c, views, nviews, pixel_out, z_out, nullptr, hash_out, device_ms);
+    return render_impl(c, views, nviews, pixel_out, z_out, nullptr, nullptr, hash_out, device_ms);
 }
 
 int gelcu_render_rgb8(gelcu_ctx* c, const gelcu_view* views, int nviews, uint8_t* rgb_out, uint64_t* hash_out, float* device_ms)
 {
     if(!rgb_out && nviews > 0) return fail(GELCU_E_INVALID, "null rgb_out");
-    return render_impl(c, views, nviews, nullptr, nullptr, rgb_out, hash_out, device_ms);
+    return render_impl(c, views, nviews, nullptr, nullptr, rgb_out, nullptr, hash_out, device_ms);
+}
+
+int gelcu_render_region(gelcu_ctx* c, const gelcu_view* views, int nviews, void* pixel_io, float* z_io,
+                        gelcu_rect* rect_io, int rgb8, uint64_t* hash_out, float* device_ms)
+{
+    if(nviews > 0 && (!pixel_io || !rect_io)) return fail(GELCU_E_INVALID, "gelcu_render_region needs pixel_io and rect_io");
+    if(rgb8 && z_io) return fail(GELCU_E_INVALID, "z_io must be NULL with rgb8 output");
+    if(rgb8) return render_impl(c, views, nviews, nullptr, nullptr, (uint8_t*) pixel_io, rect_io, hash_out, device_ms);
+    return render_impl(c, views, nviews, (uint32_t*) pixel_io, z_io, nullptr, rect_io, hash_out, device_ms);
 }
 
 int gelcu_read_frame(gelcu_ctx* c, int slot, uint32_t* pixel_out, float* z_out)
@@ -686,8 +939,12 @@ void gelcu_destroy(gelcu_ctx* c)
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
     if(c->h_vinit) cudaFreeHost(c->h_vinit);
+    if(c->h_vstat) cudaFreeHost(c->h_vstat);
     for(cudaEvent_t e : c->ev) cudaEventDestroy(e);
-    for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); }
+    for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); if(c->stats_ready[k]) cudaEventDestroy(c->stats_ready[k]); }
+    if(c->hi_stream) cudaStreamDestroy(c->hi_stream);
+    if(c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if(c->stats_go) cudaEventDestroy(c->stats_go);
     if(c->stream) cudaStreamDestroy(c->stream);
     if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if(c->side_stream) cudaStreamDestroy(c->side_stream);

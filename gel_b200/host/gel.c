@@ -101,7 +101,7 @@ int main(int argc, char* argv[])
     if(rc == -1) { printf("could not open %s\n", positional[0]); exit(1); }
     if(rc != 0) { printf("could not parse %s (error %d)\n", positional[0], rc); exit(1); }
     rc = gel_bmp_load(positional[1], &tex);
-    if(rc != 0) { printf("could not load %s (error %d; need a 24-bit uncompressed BMP)\n", positional[1], rc); exit(1); }
+    if(rc != 0) { printf("could not load %s (error %d; need an uncompressed 8-, 24- or 32-bit BMP)\n", positional[1], rc); exit(1); }
 
     /* scripted input -> one basis per frame (main.c:501, 506-512) */
     const int nviews = sweep > 0 ? sweep : frames;

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <stdint.h>
 
 typedef struct { float* p; size_t n, cap; } FVec;
 typedef struct { int* p; size_t n, cap; } IVec;
@@ -97,8 +98,9 @@ static void* parse_chunk(void* arg)
             int q[9];
             if(scan_face(line + 1, q) == 9)
             {
-                for(int k = 0; k < 9; k++) q[k] -= 1;
-                rc = ivec_push9(&j->fs, q);
+                /* file order v/t/n per corner -> the reference's Face { va,vb,vc, ta,tb,tc, na,nb,nc }, 0-based (main.c:165-170) */
+                const int face[9] = { q[0] - 1, q[3] - 1, q[6] - 1, q[1] - 1, q[4] - 1, q[7] - 1, q[2] - 1, q[5] - 1, q[8] - 1 };
+                rc = ivec_push9(&j->fs, face);
             }
             else rc = -2;
         }
@@ -122,19 +124,20 @@ static void* expand_range(void* arg)
     for(int i = j->first; i < j->last; i++)
         for(int k = 0; k < 3; k++)
         {
-            const int* q = j->fs + 9 * (size_t) i + 3 * k;   /* v, t, n of corner k */
-            if(q[0] < 0 || q[0] >= j->nv || q[1] < 0 || q[1] >= j->nvt || q[2] < 0 || q[2] >= j->nvn) { j->rc = -2; return NULL; }
+            const int* face = j->fs + 9 * (size_t) i;
+            const int qv = face[k], qt = face[3 + k], qn = face[6 + k];   /* v, t, n of corner k */
+            if(qv < 0 || qv >= j->nv || qt < 0 || qt >= j->nvt || qn < 0 || qn >= j->nvn) { j->rc = -2; return NULL; }
             for(int e = 0; e < 3; e++)
             {
-                j->tv[9 * (size_t) i + 3 * k + e] = j->vs[3 * q[0] + e] * j->inv;
-                j->tt[9 * (size_t) i + 3 * k + e] = j->ts[3 * q[1] + e];
-                j->tn[9 * (size_t) i + 3 * k + e] = j->ns[3 * q[2] + e];
+                j->tv[9 * (size_t) i + 3 * k + e] = j->vs[3 * qv + e] * j->inv;
+                j->tt[9 * (size_t) i + 3 * k + e] = j->ts[3 * qt + e];
+                j->tn[9 * (size_t) i + 3 * k + e] = j->ns[3 * qn + e];
             }
         }
     return NULL;
 }
 
-int gel_obj_load(const char* path, GelMesh* out)
+int gel_obj_parse(const char* path, GelObj* out)
 {
     memset(out, 0, sizeof *out);
     FILE* f = fopen(path, "r");
@@ -207,7 +210,27 @@ int gel_obj_load(const char* path, GelMesh* out)
     for(int t = 0; t < nthreads; t++) { free(jobs[t].vs.p); free(jobs[t].ns.p); free(jobs[t].ts.p); free(jobs[t].fs.p); }
     if(rc) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return rc == -2 ? -2 : -3; }
 
-    const int nv = (int) (vs.n / 3), nvn = (int) (ns.n / 3), nvt = (int) (ts.n / 3), nt = (int) (fs.n / 9);
+    out->v = vs.p; out->vn = ns.p; out->vt = ts.p; out->faces = fs.p;
+    out->nv = (int) (vs.n / 3); out->nvn = (int) (ns.n / 3); out->nvt = (int) (ts.n / 3); out->nfaces = (int) (fs.n / 9);
+    out->parse_threads = nthreads;
+    return 0;
+}
+
+void gel_obj_free(GelObj* o)
+{
+    free(o->v); free(o->vt); free(o->vn); free(o->faces);
+    memset(o, 0, sizeof *o);
+}
+
+int gel_obj_expand(const GelObj* obj, GelMesh* out)
+{
+    memset(out, 0, sizeof *out);
+    int rc = 0;
+    pthread_t tid[PARSE_MAX_THREADS];
+    const int nthreads = obj->parse_threads > 0 ? obj->parse_threads : 1;
+    const FVec vs = { obj->v, 0, 0 }, ns = { obj->vn, 0, 0 }, ts = { obj->vt, 0, 0 };
+    const IVec fs = { obj->faces, 0, 0 };
+    const int nv = obj->nv, nvn = obj->nvn, nvt = obj->nvt, nt = obj->nfaces;
     /* vmaxlen (main.c:233-240) and tvgen's integer scale (main.c:244) */
     float maxlen = 0.0f;
     for(int i = 0; i < nv; i++)
@@ -217,7 +240,7 @@ int gel_obj_load(const char* path, GelMesh* out)
         if(len > maxlen) maxlen = len;
     }
     const int scale = (int) maxlen;
-    if(nt > 0 && scale == 0) { free(vs.p); free(ns.p); free(ts.p); free(fs.p); return -4; }
+    if(nt > 0 && scale == 0) return -4;
     const float inv = nt > 0 ? 1.0f / scale : 1.0f;
     const size_t soup_tris = nt > 0 ? (size_t) nt : 1;
     out->tv = (float*) malloc(sizeof(float) * 9 * soup_tris);
@@ -246,10 +269,19 @@ int gel_obj_load(const char* path, GelMesh* out)
         for(int t = 1; t <= started; t++) pthread_join(tid[t], NULL);
         for(int t = 0; t < nexp; t++) if(ej[t].rc) rc = ej[t].rc;
     }
-    free(vs.p); free(ns.p); free(ts.p); free(fs.p);
     if(rc) { gel_mesh_free(out); return rc; }
     out->ntri = nt; out->nv = nv; out->nvt = nvt; out->nvn = nvn;
     return 0;
+}
+
+int gel_obj_load(const char* path, GelMesh* out)
+{
+    GelObj obj;
+    memset(out, 0, sizeof *out);
+    int rc = gel_obj_parse(path, &obj);
+    if(rc == 0) rc = gel_obj_expand(&obj, out);
+    gel_obj_free(&obj);
+    return rc;
 }
 
 void gel_mesh_free(GelMesh* m)
@@ -260,6 +292,10 @@ void gel_mesh_free(GelMesh* m)
 
 static uint32_t le32(const unsigned char* p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t) p[3] << 24; }
 
+/* Uncompressed Windows BMP -> XRGB8888 top-down with the X byte 0, i.e. what the reference gets from
+ * IMG_Load + SDL_ConvertSurface(RGB888) (main.c:473-480): 24-bit BGR, 32-bit BGRX/BGRA (alpha dropped by the
+ * conversion) and 8-bit palettised (palette entries B, G, R, -).  Every size read from the file is validated against
+ * the file length before anything is allocated or read. */
 int gel_bmp_load(const char* path, GelTexture* out)
 {
     memset(out, 0, sizeof *out);
@@ -267,26 +303,52 @@ int gel_bmp_load(const char* path, GelTexture* out)
     if(!f) return -1;
     unsigned char hdr[54];
     if(fread(hdr, 1, 54, f) != 54 || hdr[0] != 'B' || hdr[1] != 'M') { fclose(f); return -2; }
-    const uint32_t data_off = le32(hdr + 10);
+    if(fseek(f, 0, SEEK_END) != 0) { fclose(f); return -4; }
+    const long flen = ftell(f);
+    const uint32_t data_off = le32(hdr + 10), dib = le32(hdr + 14), comp = le32(hdr + 30);
     const int32_t w = (int32_t) le32(hdr + 18), hs = (int32_t) le32(hdr + 22);
     const int bpp = hdr[28] | hdr[29] << 8;
-    if(bpp != 24 || le32(hdr + 30) != 0 || w <= 0 || hs == 0) { fclose(f); return -2; }
-    const int h = hs < 0 ? -hs : hs;
-    const size_t stride = ((size_t) w * 3 + 3) & ~(size_t) 3;
+    /* BI_RGB, or BI_BITFIELDS on 32 bits (the masks SDL writes: the layout is still B, G, R, A in memory) */
+    const int layout_ok = comp == 0 || (comp == 3 && bpp == 32);
+    if(dib < 40 || !layout_ok || (bpp != 8 && bpp != 24 && bpp != 32) || w <= 0 || hs == 0 || hs == INT32_MIN) { fclose(f); return -2; }
+    const size_t h = (size_t) (hs < 0 ? -(int64_t) hs : hs);
+    if((size_t) w > (size_t) 1 << 15 || h > (size_t) 1 << 15) { fclose(f); return -2; }          /* 32768^2 texels at most */
+    const size_t stride = ((size_t) w * (size_t) (bpp / 8) + 3) & ~(size_t) 3;
+    if(flen < 54 || (size_t) data_off < 14 + (size_t) dib || (size_t) data_off > (size_t) flen || stride * h > (size_t) flen - data_off) { fclose(f); return -4; }
+    uint32_t palette[256];
+    memset(palette, 0, sizeof palette);
+    if(bpp == 8)
+    {
+        uint32_t ncol = le32(hdr + 46);
+        if(ncol == 0 || ncol > 256) ncol = 256;
+        const size_t pal_off = 14 + (size_t) dib;
+        if(pal_off + 4 * (size_t) ncol > (size_t) data_off) ncol = (uint32_t) (((size_t) data_off - pal_off) / 4);
+        unsigned char quad[4];
+        if(fseek(f, (long) pal_off, SEEK_SET) != 0) { fclose(f); return -4; }
+        for(uint32_t k = 0; k < ncol; k++)
+        {
+            if(fread(quad, 1, 4, f) != 4) { fclose(f); return -4; }
+            palette[k] = (uint32_t) quad[2] << 16 | (uint32_t) quad[1] << 8 | quad[0];
+        }
+    }
     unsigned char* row = (unsigned char*) malloc(stride);
     uint32_t* px = (uint32_t*) malloc(sizeof(uint32_t) * (size_t) w * h);
     if(!row || !px) { free(row); free(px); fclose(f); return -3; }
-    fseek(f, (long) data_off, SEEK_SET);
-    for(int r = 0; r < h; r++)
+    if(fseek(f, (long) data_off, SEEK_SET) != 0) { free(row); free(px); fclose(f); return -4; }
+    for(size_t r = 0; r < h; r++)
     {
         if(fread(row, 1, stride, f) != stride) { free(row); free(px); fclose(f); return -4; }
-        uint32_t* dst = px + (size_t) (hs < 0 ? r : h - 1 - r) * w;    /* file is bottom-up unless height < 0 */
-        for(int x = 0; x < w; x++)
-            dst[x] = (uint32_t) row[3 * x + 2] << 16 | (uint32_t) row[3 * x + 1] << 8 | row[3 * x];   /* X byte = 0 */
+        uint32_t* dst = px + (hs < 0 ? r : h - 1 - r) * (size_t) w;    /* file is bottom-up unless height < 0 */
+        if(bpp == 24)
+            for(int32_t x = 0; x < w; x++) dst[x] = (uint32_t) row[3 * x + 2] << 16 | (uint32_t) row[3 * x + 1] << 8 | row[3 * x];   /* X byte = 0 */
+        else if(bpp == 32)
+            for(int32_t x = 0; x < w; x++) dst[x] = (uint32_t) row[4 * x + 2] << 16 | (uint32_t) row[4 * x + 1] << 8 | row[4 * x];
+        else
+            for(int32_t x = 0; x < w; x++) dst[x] = palette[row[x]];
     }
     free(row);
     fclose(f);
-    out->pixels = px; out->w = w; out->h = h;
+    out->pixels = px; out->w = w; out->h = (int) h;
     return 0;
 }
 

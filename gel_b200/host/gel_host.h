@@ -3,7 +3,7 @@
  *
  *   gel_obj_load      oload + oparse + tvgen/ttgen/tngen     main.c:460-469, 84-180, 227-286   (files > 4 MB: parsed in
  *                     line-aligned chunks by up to 32 threads, GEL_PARSE_THREADS overrides; same arrays as one pass)
- *   gel_bmp_load      sload (IMG_Load + convert to RGB888)    main.c:471-484   (24-bit BMP only, no SDL_image)
+ *   gel_bmp_load      sload (IMG_Load + convert to RGB888)    main.c:471-484   (uncompressed 8/24/32-bit BMP, no SDL_image)
  *   gel_view_basis    camera basis from (xt, yt)              main.c:506-512
  *   gel_input_step    ipump's angle update                    main.c:408-409
  *   gel_upright       schurn's -90 degree rotation            main.c:424-432   (for image export)
@@ -30,6 +30,18 @@ typedef struct
 }
 GelMesh;
 
+/* The indexed OBJ as the reference holds it after oparse (main.c:129-180, the `Obj` struct at :37-43): three floats per
+ * v / vt / vn line and one `Face` per f line -- 9 ints { va,vb,vc, ta,tb,tc, na,nb,nc }, 0-based (main.c:22-28,165-170).
+ * This is what gelcu_set_mesh_indexed takes: the soups (main.c:242-286) are then generated on the device. */
+typedef struct
+{
+    float *v, *vt, *vn;
+    int* faces;
+    int nv, nvt, nvn, nfaces;
+    int parse_threads;      /* threads the parse used (gel_obj_expand reuses the count) */
+}
+GelObj;
+
 typedef struct { uint32_t* pixels; int w, h; } GelTexture;   /* XRGB8888 top-down, pitch 4*w */
 
 /* 0 on success; -1 cannot open, -2 malformed (index out of range, no faces' data), -3 out of memory,
@@ -37,7 +49,14 @@ typedef struct { uint32_t* pixels; int w, h; } GelTexture;   /* XRGB8888 top-dow
 int  gel_obj_load(const char* path, GelMesh* out);
 void gel_mesh_free(GelMesh* m);
 
-/* 0 on success; -1 cannot open, -2 not a 24-bit uncompressed BMP, -3 out of memory, -4 truncated. */
+/* The two halves of gel_obj_load: text -> indexed arrays (oparse), indexed arrays -> soups (tvgen/ttgen/tngen on the
+ * host).  gel_obj_parse alone + gelcu_set_mesh_indexed skips the host expansion.  Same return codes. */
+int  gel_obj_parse(const char* path, GelObj* out);
+int  gel_obj_expand(const GelObj* obj, GelMesh* out);
+void gel_obj_free(GelObj* o);
+
+/* 0 on success; -1 cannot open, -2 not an uncompressed 8/24/32-bit BMP (or larger than 32768 per side),
+ * -3 out of memory, -4 truncated / inconsistent header. */
 int  gel_bmp_load(const char* path, GelTexture* out);
 void gel_texture_free(GelTexture* t);
 

@@ -76,6 +76,17 @@ int gelcu_create(gelcu_ctx** ctx, int device, int xres, int yres);
  * main.c:8-12,45-49).  Copied; the caller may free its arrays.  ntri may be 0. */
 int gelcu_set_mesh(gelcu_ctx* ctx, const float* tv, const float* tn, const float* tt, int ntri);
 
+/* Mesh, indexed: the OBJ arrays as the reference holds them after oparse (main.c:129-180) --
+ *   v / vt / vn   3 floats per `v`, `vt`, `vn` line (the reference's Vertices.vertex, main.c:8-20); v is UNSCALED
+ *   faces         the reference's Face array (main.c:22-28): 9 ints { va,vb,vc, ta,tb,tc, na,nb,nc }, 0-based
+ * and replaces vmaxlen + tvgen / ttgen / tngen (main.c:233-286): the scale 1.0f / (int) max|v| and the per-corner
+ * gathers run on the device (one multiply per component, bit-identical to tvgen's tmul), corners are merged per
+ * (position, normal) index pair, and the host never builds or re-hashes the 108-byte-per-triangle soups.
+ * Frames are bit-identical to gelcu_set_mesh on the soups the reference would have generated.  Errors:
+ * GELCU_E_INVALID for an index outside its array or max|v| < 1 (the reference divides by (int) 0, main.c:244,253). */
+int gelcu_set_mesh_indexed(gelcu_ctx* ctx, const float* v, int nv, const float* vt, int nvt, const float* vn, int nvn,
+                           const int* faces, int nfaces);
+
 /* Texture = fdif->pixels / w / h (main.c:359-361,366): XRGB8888, top-down, pitch 4*w.  Copied. */
 int gelcu_set_texture(gelcu_ctx* ctx, const uint32_t* xrgb, int w, int h);
 
@@ -103,6 +114,25 @@ int gelcu_render(gelcu_ctx* ctx, const gelcu_view* views, int nviews,
  *              the sink kernel, like it excludes copies). */
 int gelcu_render_rgb8(gelcu_ctx* ctx, const gelcu_view* views, int nviews,
                       uint8_t* rgb_out, uint64_t* hash_out, float* device_ms);
+
+/* Region output: only the part of each frame the mesh can touch crosses PCIe.
+ * A view's REGION is the screen bounding box of its transformed vertices (every bbox of main.c:344-347 lies inside it),
+ * clipped to the frame and widened to multiples of 8; everything outside holds the reset values of main.c:413-417
+ * (pixel 0, z -FLT_MAX).  gelcu_render_region copies just that rectangle of every frame into the caller's full-size
+ * frames and keeps the rest of each frame correct with a dirty-rectangle contract:
+ *   rect_io[k] in   the part of frame k of pixel_io / z_io that may currently hold non-reset values:
+ *                   x1 < x0 = none (the frame is all reset values, e.g. a zeroed pixel buffer);
+ *                   { 0, 0, xres-1, yres-1 } = anything (the library resets the whole frame on the host);
+ *                   or the rectangle a previous call returned for this frame slot -- then only the strips that the
+ *                   old rectangle covers and the new one does not are reset, on the host, while the copies run
+ *   rect_io[k] out  the view's region (inclusive; x1 < x0 when the mesh is off screen)
+ * On return every frame is complete and bit-identical to what gelcu_render writes.  rgb8 = 0: pixel_io (and z_io, may
+ * be NULL) are sideways frames as in gelcu_render; rgb8 = 1: pixel_io is the upright 24-bit layout of
+ * gelcu_render_rgb8 (z_io must be NULL).  This is the reference's own frame loop pattern -- one canvas reused every
+ * frame (slock/sunlock, main.c:504,523) -- without re-sending the background each time. */
+typedef struct { int x0, y0, x1, y1; } gelcu_rect;
+int gelcu_render_region(gelcu_ctx* ctx, const gelcu_view* views, int nviews, void* pixel_io, float* z_io,
+                        gelcu_rect* rect_io, int rgb8, uint64_t* hash_out, float* device_ms);
 
 /* Copies frame `slot` (0-based within the LAST batch of the previous gelcu_render) to the host. */
 int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out);

@@ -16,12 +16,20 @@ NTHREADS = max(1, min(os.cpu_count() or 1, 64))
 FLT_MIN = np.finfo(np.float32).min
 
 
-PIPELINE = int(os.environ.get("GELCU_PIPELINE", "0"))      # 0 = library's choice, 1 = tile pipeline, 2 = direct pipeline
+PIPELINE = 0      # set per test by the `pipeline` fixture: 0 = the library's choice, 1 = tile pipeline, 2 = direct pipeline
+
+
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "tile", "direct"], autouse=True)
+def pipeline(request):
+    """Every test of this module runs three times -- with the pipeline the library picks from the mesh, with the tile
+    pipeline forced and with the direct pipeline forced: all three must be bit-exact on every input."""
+    global PIPELINE
+    PIPELINE = request.param
+    yield request.param
+    PIPELINE = 0
 
 
 def make_renderer(xres, yres, tv, tn, tt, tex):
-    """Every test runs with the pipeline the library picks, or with the one forced by GELCU_PIPELINE (the GPU
-    scripts run the suite three times: auto, tile, direct -- all three must be bit-exact)."""
     r = gel_b200.Renderer(xres, yres)
     r.set_mesh(tv, tn, tt)
     r.set_texture(tex)
@@ -358,6 +366,188 @@ def test_wide_and_compact_shading_records_agree(cfg1):
             r.set_mesh(tv, tn, tt); r.set_texture(tex); r.set_option("pipeline", 2)
             out = r.render(bases, z=True, hashes=True)
             assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])) and np.array_equal(out["hash"], ref["hash"])
+
+
+# ---- indexed mesh entry: soups generated on the device ---------------------------------
+
+def test_indexed_mesh_equals_the_soup_mesh(cfg1_paths, cfg1):
+    """gelcu_set_mesh_indexed on the OBJ's arrays == gelcu_set_mesh on the soups the host expands from them
+    (vmaxlen / (int) scale / tvgen / ttgen / tngen, main.c:233-286): same frames, same merged vertex count."""
+    tv, tn, tt, tex = cfg1
+    v, vt, vn, faces = gel_b200.load_obj_indexed(cfg1_paths[0])
+    assert faces.shape == (5000, 9) and v.shape == (2601, 3)
+    bases = gel_b200.view_bases([(0, 0), (0.9, 0.2), (3.5, -0.1)])
+    ref = oracle.render_views(tv, tn, tt, tex, 640, 480, bases, nthreads=NTHREADS, z=True, hashes=True)
+    with gel_b200.Renderer(640, 480) as r:
+        r.set_mesh_indexed(v, vt, vn, faces); r.set_texture(tex)
+        if PIPELINE:
+            r.set_option("pipeline", PIPELINE)
+        out = r.render(bases, z=True, hashes=True)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])) and np.array_equal(out["hash"], ref["hash"])
+        vew, shade = r.debug_transform(bases[1])
+        rvew, _ = oracle.transform(tv, tn, bases[1], 640, 480)
+        assert np.array_equal(bits(vew), bits(rvew))
+        assert r.stats()["unique_vertices"] == len({(int(a), int(b)) for a, b in zip(faces[:, 0:3].ravel(), faces[:, 6:9].ravel())})
+        r.set_mesh(tv, tn, tt)                                            # and back to the soup entry on the same context
+        again = r.render(bases, hashes=True)
+        assert np.array_equal(again["hash"], ref["hash"])
+
+
+def test_indexed_mesh_hard_edges_scale_and_errors():
+    """A position paired with several normals (hard edges) becomes several merged vertices; max|v| = 2.9 scales by
+    1.0f / (int) 2 as tvgen does (main.c:244,253); bad indices and max|v| < 1 are refused."""
+    rng = np.random.default_rng(12)
+    nv, nn, nt, nf = 40, 25, 30, 300
+    v = rng.uniform(-1, 1, (nv, 3)).astype(np.float32); v[:, 1] = np.abs(v[:, 1]) * 0.8 + 0.1; v[:, 2] *= 0.3
+    v[7] = (2.0, 2.0, 0.7)                                                # |v| = 2.91 -> scale 2
+    vn = rng.normal(size=(nn, 3)).astype(np.float32); vn /= np.linalg.norm(vn, axis=1, keepdims=True)
+    vt = np.zeros((nt, 3), np.float32); vt[:, :2] = rng.uniform(0, 1, (nt, 2)); vt[:, 2] = 9.0      # uv.z is never read
+    faces = np.concatenate([rng.integers(0, nv, (nf, 3)), rng.integers(0, nt, (nf, 3)), rng.integers(0, nn, (nf, 3))], 1).astype(np.int32)
+    inv = np.float32(1.0) / np.float32(int(np.sqrt((v.astype(np.float32) ** 2).sum(1)).max()))
+    tv = (v[faces[:, 0:3]] * inv).astype(np.float32).reshape(nf, 9)
+    tt = vt[faces[:, 3:6]].reshape(nf, 9); tn = vn[faces[:, 6:9]].reshape(nf, 9)
+    tex = small_tex(rng, 32, 32)
+    bases = gel_b200.view_bases([(0, 0), (0.3, 0.1)])
+    ref = oracle.render_views(tv, tn, tt, tex, 320, 240, bases, z=True, hashes=True)
+    with gel_b200.Renderer(320, 240) as r:
+        r.set_mesh_indexed(v, vt, vn, faces); r.set_texture(tex)
+        if PIPELINE:
+            r.set_option("pipeline", PIPELINE)
+        out = r.render(bases, z=True, hashes=True)
+        assert out["rc"] == (1 if ref["clipped"] else 0)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])) and np.array_equal(out["hash"], ref["hash"])
+        assert r.stats()["unique_vertices"] == len({(int(a), int(b)) for a, b in zip(faces[:, 0:3].ravel(), faces[:, 6:9].ravel())}) > nv
+        bad = faces.copy(); bad[5, 7] = nn                                # normal index one past the end
+        with pytest.raises(gel_b200.GelcuError) as e:
+            r.set_mesh_indexed(v, vt, vn, bad)
+        assert e.value.code == gel_b200.GELCU_E_INVALID
+        with pytest.raises(gel_b200.GelcuError):                          # a failed load leaves NO mesh behind
+            r.render(bases)
+        with pytest.raises(gel_b200.GelcuError):
+            r.set_mesh_indexed(v * np.float32(0.2), vt, vn, faces)        # max|v| < 1: (int) maxlen == 0
+        r.set_mesh_indexed(v, vt, vn, faces[:0])                          # no faces: cleared frames
+        assert not r.render(bases)["pixel"].any()
+
+
+def test_indexed_mesh_cfg3(cfg3_inputs, tmp_path):
+    """Full size: the 1 M-triangle OBJ through the indexed entry, device checksums against the soup entry."""
+    tv, tn, tt, tex = cfg3_inputs
+    obj = str(tmp_path / "sphere707.obj")
+    open(obj, "w").write(synth.sphere_obj_text(707, 707))
+    v, vt, vn, faces = gel_b200.load_obj_indexed(obj)
+    bases = gel_b200.view_bases(synth.view_angles(64)[[3, 30]])
+    with make_renderer(3840, 2160, tv, tn, tt, tex) as r:
+        want = r.render(bases, pixels=False, hashes=True)
+        nu = r.stats()["unique_vertices"]
+        r.set_mesh_indexed(v, vt, vn, faces)
+        got = r.render(bases, pixels=False, hashes=True)
+        assert np.array_equal(got["hash"], want["hash"])
+        assert nu <= r.stats()["unique_vertices"] <= 501264              # the soup entry also merges equal-valued corners (seam, poles)
+
+
+# ---- region output (dirty-rectangle contract) --------------------------------------------------------------
+
+@pytest.mark.parametrize("rgb8", [False, True])
+def test_render_region_keeps_frames_complete(rgb8):
+    """gelcu_render_region into ONE reused set of frame slots: views whose regions move, shrink and grow; a slot that starts
+    as garbage with an "anything" rectangle; an empty mesh at the end.  After every call each frame must equal the oracle's."""
+    rng = np.random.default_rng(505)
+    tv, tn, tt = random_soup(rng, 900, size=(0.004, 0.05), xr=(-0.1, 0.45), yr=(0.25, 0.8), zspread=0.4)      # lopsided: the region moves with the view
+    tex = small_tex(rng, 64, 64)
+    W, H, n = 456, 344, 5
+    calls = [[(0, 0), (0.5, 0.1), (-0.6, -0.1), (1.2, 0.05), (2.4, 0.0)], [(3.1, 0.1), (-1.5, 0.0), (0.2, 0.3), (0.0, 0.0), (0.7, -0.2)],
+             [(0.1, 0.0), (0.1, 0.0), (2.0, 0.1), (-2.0, 0.1), (1.0, 0.0)]]
+    with make_renderer(W, H, tv, tn, tt, tex) as r:
+        r.set_option("batch_views", 2)                                   # several batches per call, both frame buffers
+        frames = np.full((n, H, W, 3), 0xAB, np.uint8) if rgb8 else np.full((n, W * H), 0xDEADBEEF, np.uint32)
+        zs = None if rgb8 else np.full((n, W * H), 7.0, np.float32)
+        rects = np.tile(np.array([0, 0, W - 1, H - 1], np.int32), (n, 1))       # "anything": the library resets the whole frame
+        for angles in calls:
+            bases = gel_b200.view_bases(angles)
+            ref = oracle.render_views(tv, tn, tt, tex, W, H, bases, nthreads=NTHREADS, z=True, hashes=True)
+            out = r.render_region(bases, frames, rects, z_io=zs, rgb8=rgb8, hashes=True)
+            assert out["rc"] == (1 if ref["clipped"] else 0) and np.array_equal(out["hash"], ref["hash"])
+            for k in range(n):
+                lit = np.argwhere(ref["z"][k].reshape(W, H) != FLT_MIN)
+                x0, y0, x1, y1 = rects[k]
+                assert x0 % 8 == 0 and y0 % 8 == 0 and x0 <= lit[:, 0].min() and lit[:, 0].max() <= x1 and y0 <= lit[:, 1].min() and lit[:, 1].max() <= y1
+                if rgb8:
+                    assert np.array_equal(frames[k], upright_rgb(ref["pixel"][k], W, H)), f"view {k}"
+                else:
+                    assert np.array_equal(frames[k], ref["pixel"][k]) and np.array_equal(bits(zs[k]), bits(ref["z"][k])), f"view {k}"
+            assert r.stats()["d2h_bytes"] < 0.8 * n * W * H * (3 if rgb8 else 8)      # less than the full frames crossed PCIe
+        empty = np.zeros((0, 9), np.float32)
+        r.set_mesh(empty, empty, empty)
+        out = r.render_region(gel_b200.view_bases(calls[0]), frames, rects, z_io=zs, rgb8=rgb8)
+        assert not frames.any() and (rects[:, 2] < rects[:, 0]).all() and (zs is None or (zs == FLT_MIN).all())
+
+
+def test_render_region_cfg2_sweep(cfg1):
+    """The cfg-2 sweep through one reused canvas (the reference's own pattern: one streaming texture, main.c:504,523):
+    every frame complete, a fraction of the bytes copied."""
+    tv, tn, tt, tex = cfg1
+    ang = synth.view_angles(360)[::9]                                     # 40 views
+    W, H = 1920, 1080
+    ref = oracle.render_views(tv, tn, tt, tex, W, H, gel_b200.view_bases(ang), nthreads=NTHREADS)
+    with make_renderer(W, H, tv, tn, tt, tex) as r:
+        canvas = np.zeros((1, W * H), np.uint32)
+        rect = np.array([[0, 0, -1, -1]], np.int32)                       # a zeroed canvas holds nothing
+        moved = 0
+        for k in range(len(ang)):
+            r.render_region(gel_b200.view_bases(ang[k:k + 1]), canvas, rect)
+            assert np.array_equal(canvas[0], ref["pixel"][k]), f"view {k}"
+            moved += r.stats()["d2h_bytes"]
+        assert moved < 0.5 * len(ang) * 4 * W * H
+
+
+def test_contexts_sharded_like_ranks_match_one_context(cfg1):
+    """N contexts, each rendering its shard of the view list (contiguous blocks, gel_b200.shard_views) from its own
+    host thread -- on N devices when the box has them, else all on device 0 -- give the per-view checksums of ONE context
+    rendering the whole list: a frame depends only on mesh, texture and (xt, yt) (main.c:509-522)."""
+    import threading
+    tv, tn, tt, tex = cfg1
+    n, world = 96, 4
+    bases = gel_b200.view_bases(synth.view_angles(n))
+    ndev = max(1, gel_b200.cu().gelcu_device_count())
+    with make_renderer(1024, 768, tv, tn, tt, tex) as r:
+        whole = r.render(bases, pixels=False, hashes=True)["hash"]
+    parts, errors = [None] * world, []
+
+    def shard(rank):
+        try:
+            lo, hi = gel_b200.shard_views(n, world, rank)
+            with gel_b200.Renderer(1024, 768, device=rank % ndev) as q:
+                q.set_mesh(tv, tn, tt); q.set_texture(tex)
+                if PIPELINE:
+                    q.set_option("pipeline", PIPELINE)
+                parts[rank] = q.render(bases[lo:hi], pixels=False, hashes=True)["hash"]
+        except Exception as e:                                            # noqa: BLE001 -- surfaced below
+            errors.append(e)
+
+    ts = [threading.Thread(target=shard, args=(k,)) for k in range(world)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors
+    assert np.array_equal(np.concatenate(parts), whole)
+    ref = oracle.render_views(tv, tn, tt, tex, 1024, 768, bases[::16], nthreads=NTHREADS, pixels=False, hashes=True)
+    assert np.array_equal(whole[::16], ref["hash"])
+
+
+def test_non_finite_vertices_match_the_oracle():
+    """NaN / inf / huge coordinates in a few triangles: a NaN depth never passes `z > zbuff` (main.c:356) and den = NaN never
+    draws; the rest of the scene is untouched.  Compared where x86's and CUDA's float->int conversions agree (no NaN in x / y)."""
+    rng = np.random.default_rng(99)
+    tv, tn, tt = random_soup(rng, 400, size=(0.01, 0.12), xr=(-0.3, 0.3), yr=(0.1, 0.9))
+    tv = tv.reshape(-1, 3, 3).copy()
+    tv[3, 0, 2] = np.inf; tv[9, 1, 2] = -np.inf; tv[20, 2, 2] = np.nan; tv[31, :, 2] = np.nan
+    tv[40, 0, 2] = 3.0e38; tv[40, 1, 2] = -3.0e38                          # finite, but the three-term depth sum can overflow
+    tv = tv.reshape(-1, 9)
+    tex = small_tex(rng, 16, 16)
+    bases = gel_b200.view_bases([(0, 0), (0.2, 0.05)])
+    with make_renderer(320, 240, tv, tn, tt, tex) as r:
+        out = r.render(bases, z=True, hashes=True)
+        ref = oracle.render_views(tv, tn, tt, tex, 320, 240, bases, z=True, hashes=True)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"]))
+        assert not np.isnan(out["z"]).any()
 
 
 def test_call_order_and_argument_errors():

@@ -86,6 +86,57 @@ def test_bmp_padding_and_topdown(tmp_path):
         gel_b200.load_bmp(str(tmp_path / "nope.bmp"))
 
 
+def _bmp(w, h, bpp, body, *, palette=b"", comp=0, dib=40, off=None, ncol=0):
+    import struct
+    off = 14 + dib + len(palette) if off is None else off
+    info = struct.pack("<IiiHHIIiiII", dib, w, h, 1, bpp, comp, len(body), 0, 0, ncol, 0) + b"\0" * (dib - 40)
+    return struct.pack("<2sIHHI", b"BM", off + len(body), 0, 0, off) + info + palette + body
+
+
+def test_bmp_32bit_and_8bit_palettised_equal_the_24bit_image(tmp_path):
+    """The reference converts whatever IMG_Load returns to RGB888 (main.c:473-480): the same picture stored as 24-bit,
+    32-bit (alpha dropped; BI_RGB and BI_BITFIELDS headers) and 8-bit palettised BMP must decode to the same texels."""
+    rng = np.random.default_rng(3)
+    w, h = 5, 4
+    idx = rng.integers(0, 7, (h, w), dtype=np.uint8)                      # image as palette indices, top-down
+    pal = rng.integers(0, 256, (7, 3), dtype=np.uint8)                    # B, G, R
+    bgr = pal[idx]                                                        # (h, w, 3)
+    want = (bgr[..., 2].astype(np.uint32) << 16) | (bgr[..., 1].astype(np.uint32) << 8) | bgr[..., 0]
+    rows24 = b"".join(bgr[y].tobytes() + b"\0" * (-(3 * w) % 4) for y in range(h - 1, -1, -1))
+    rows32 = b"".join(np.concatenate([bgr[y], np.full((w, 1), 0xAB, np.uint8)], 1).tobytes() for y in range(h - 1, -1, -1))
+    rows8 = b"".join(idx[y].tobytes() + b"\0" * (-w % 4) for y in range(h - 1, -1, -1))
+    palette = b"".join(bytes(c) + b"\0" for c in pal)
+    files = {"a24": _bmp(w, h, 24, rows24), "a32": _bmp(w, h, 32, rows32), "a32bf": _bmp(w, h, 32, rows32, comp=3, dib=56),
+             "a8": _bmp(w, h, 8, rows8, palette=palette, ncol=7)}
+    for name, data in files.items():
+        p = tmp_path / f"{name}.bmp"
+        p.write_bytes(data)
+        assert np.array_equal(gel_b200.load_bmp(str(p)), want), name
+    assert np.array_equal(oracle.load_bmp(str(tmp_path / "a24.bmp")), want)
+
+
+def test_bmp_headers_are_validated_before_use(tmp_path):
+    """Sizes and offsets come from the file: none may drive an allocation or a seek before being checked."""
+    good = _bmp(4, 4, 24, b"\x11" * 48)
+    cases = {
+        "huge_w": _bmp(1 << 30, 4, 24, b"\x11" * 48),                     # w*h would overflow int arithmetic
+        "huge_h": _bmp(4, -(1 << 31), 24, b"\x11" * 48),                  # INT32_MIN has no absolute value
+        "offset_past_end": _bmp(4, 4, 24, b"\x11" * 48, off=1 << 20),
+        "truncated": good[:-20],
+        "rle": _bmp(4, 4, 8, b"\x11" * 16, palette=b"\0" * 1024, comp=1),
+        "sixteen_bit": _bmp(4, 4, 16, b"\x11" * 32),
+        "not_bmp": b"PNG" + good[3:],
+    }
+    for name, data in cases.items():
+        p = tmp_path / f"{name}.bmp"
+        p.write_bytes(data)
+        with pytest.raises(RuntimeError):
+            gel_b200.load_bmp(str(p))
+    p = tmp_path / "good.bmp"
+    p.write_bytes(good)
+    assert gel_b200.load_bmp(str(p)).shape == (4, 4)
+
+
 def test_view_basis_matches_oracle_bitwise():
     rng = np.random.default_rng(7)
     for xt, yt in [(0, 0), (0.2, 0), (np.pi, 0.1), (-1.3, 0.7)] + list(rng.uniform(-7, 7, (200, 2))):
@@ -155,3 +206,29 @@ def test_headless_gel_usage_and_errors(tmp_path):
     assert r.returncode == 1 and r.stdout.startswith("args: path/to/obj path/to/bmp")      # main.c:488-492
     r = subprocess.run([exe, str(tmp_path / "none.obj"), str(tmp_path / "none.bmp")], capture_output=True, text=True)
     assert r.returncode == 1 and r.stdout.startswith("could not open")                      # main.c:463-467
+
+
+def test_indexed_parse_expands_to_the_same_soups(cfg1_paths):
+    """gel_obj_parse returns the reference's Obj (v / vt / vn lines, Face = { va,vb,vc, ta,tb,tc, na,nb,nc } 0-based, main.c:22-28,
+    165-170); expanding it the way tvgen / ttgen / tngen do (main.c:242-286) gives gel_obj_load's soups bit for bit."""
+    v, vt, vn, faces = gel_b200.load_obj_indexed(cfg1_paths[0])
+    tv, tn, tt = gel_b200.load_obj(cfg1_paths[0])
+    assert faces.min() == 0 and faces[:, 0:3].max() == len(v) - 1
+    inv = np.float32(1.0) / np.float32(int(np.sqrt((v * v).sum(1, dtype=np.float32)).max()))
+    assert np.array_equal(bits((v[faces[:, 0:3]] * inv).reshape(-1, 9)), bits(tv))
+    assert np.array_equal(bits(vt[faces[:, 3:6]].reshape(-1, 9)), bits(tt))
+    assert np.array_equal(bits(vn[faces[:, 6:9]].reshape(-1, 9)), bits(tn))
+
+
+def test_bench_reference_arm_and_mouse_script(cfg1_paths):
+    """`bench.py --impl reference` drives the unmodified binary through the workload's own view list: the scripted integer
+    mouse steps land on the nearest multiples of 0.005 rad, and both arms print the same `config`."""
+    import bench
+    steps = np.array([[int(x) for x in l.split()] for l in bench.mouse_script("cfg1", 5, 4).splitlines()])
+    xt = -0.005 * np.cumsum(steps[:, 0])
+    assert np.allclose(xt, 2 * np.pi * (np.arange(4) + 5) / 64, atol=0.0026) and not steps[:, 1].any()
+    if oracle.ref_binary(800, 600) is None:
+        pytest.skip("oracle/_ref not built")
+    cb = bench.run_cpu_reference("cfg1", cfg1_paths[0], cfg1_paths[1], 5000, steps=1, warmup=1, frames_per_step=2, budget_s=5.0)
+    assert cb["kind"] == "reference" and cb["value"] > 0 and set(cb["single_thread_ms_per_frame"]) == {"strict_O2", "shipped_Ofast"}
+    assert bench.workload_config("cfg3", 999698)["resolution"] == "3840x2160"
