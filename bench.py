@@ -468,7 +468,9 @@ def bench_workload(name, world, rank, local_rank, workdir, steps, warmup, flush,
     lit = int((zb != np.finfo(np.float32).min).sum())
     b_alg = algorithmic_bytes(ntri, xres, yres, lit)
 
-    dev_ms, st, launches, stage, (tw0, tw1), hashes = measure_device(r, name, views, steps, warmup, rank_offset, flush, hashes=want_hashes)
+    dev_ms, st, launches, stage, (tw0, tw1), _ = measure_device(r, name, views, steps, warmup, rank_offset, flush)
+    # per-view device checksums for the rank-parity check: a separate, untimed pass (the checksum variants of the kernels hash every pixel)
+    hashes = r.render(step_bases(name, views, rank_offset), pixels=False, hashes=True)["hash"] if want_hashes else None
     clocks = sampler.window(tw0, tw1) if sampler else None
     worst_ms = max_over_ranks(dev_ms)
     total_views = sum_over_ranks(views) * steps

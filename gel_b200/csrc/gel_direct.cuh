@@ -430,11 +430,11 @@ direct_raster_kernel(DirectParams p)
 /* D5 ------------------------------------------------------------------------------------------------------------ */
 /* one pixel: the winner's barycentrics recomputed from the same operands (identical bits), shaded once */
 template<bool COMPACT>
-__device__ __forceinline__ void direct_shade(const DirectParams& p, int view, unsigned long long key, int x, int y, uint32_t& colour, float& z)
+__device__ __forceinline__ void direct_shade(const DirectParams& p, const float4* __restrict__ xf, uint32_t* vflags, float twm1, float thm1,
+                                             unsigned long long key, int x, int y, uint32_t& colour, float& z)
 {
     colour = 0u; z = -FLT_MAX;
     if(key == CLEAR_KEY) return;
-    const float4* xf = p.xf + (size_t) view * p.nuniq;
     const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
     z = gel::zkey_inv((uint32_t) (key >> 32));
     uint32_t ia, ib, ic, uvw[6];
@@ -469,10 +469,10 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, int view, un
     const float u = gel::sub(gel::sub(1.0f, v), w);
     const float uv[6] = { __uint_as_float(uvw[0]), __uint_as_float(uvw[1]), __uint_as_float(uvw[2]), __uint_as_float(uvw[3]), __uint_as_float(uvw[4]), __uint_as_float(uvw[5]) };
     int xx, yy, shading;
-    gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
-    if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
+    gel::fragment_shade_f(v, w, u, uv, a.w, b.w, c.w, twm1, thm1, xx, yy, shading);
+    if((unsigned) xx > (unsigned) (p.tw - 1) || (unsigned) yy > (unsigned) (p.th - 1))
     {
-        atomicOr(p.flags + view, FLAG_TEXCLAMP);           /* the reference reads out of bounds here (R) */
+        atomicOr(vflags, FLAG_TEXCLAMP);                   /* the reference reads out of bounds here (R) */
         xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
     }
     colour = gel::pshade(__ldg(p.tex + (uint32_t) (xx + yy * p.tw)), shading);
@@ -518,7 +518,7 @@ direct_fill_kernel(DirectParams p)
  * evict-first in L2. */
 template<bool HASH, bool HINT>
 __global__ void __launch_bounds__(256)
-direct_fill_persistent_kernel(DirectParams p)
+direct_fill_persistent_kernel(DirectParams p, int sleep_ns)
 {
     const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
     const uint32_t zc = 0xFF7FFFFFu;                                   /* -FLT_MAX */
@@ -561,6 +561,9 @@ direct_fill_persistent_kernel(DirectParams p)
                 if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(0u, idx); hz += gel::salt_mix(zc, idx); }
             }
         }
+        /* pacing: at full speed these stores saturate DRAM and every memory operation of the raster kernel beside them
+         * queues behind them; spread over the near pass's duration they take a quarter of the bandwidth */
+        if(sleep_ns > 0) __nanosleep((unsigned) sleep_ns);
     }
     flush_hash();
 }
@@ -580,10 +583,15 @@ direct_resolve_kernel(DirectParams p)
     int rx0, rx1, ry0, ry1;
     if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
     unsigned long long hp = 0, hz = 0;
+    /* per-view bases and the texture extents as floats ((float) (w - 1), (float) (h - 1) of main.c:360-361: the same
+     * conversions, done once) live outside the pixel loop; inside it everything is a 32-bit offset from them */
     const size_t frame = (size_t) p.xres * p.yres;
-    unsigned long long* vkeys = p.keys + (size_t) view * frame;
-    uint32_t* vpixel = p.pixel + (size_t) view * frame;
-    float* vz = p.zbuf + (size_t) view * frame;
+    unsigned long long* __restrict__ vkeys = p.keys + (size_t) view * frame;
+    uint32_t* __restrict__ vpixel = p.pixel + (size_t) view * frame;
+    float* __restrict__ vz = p.zbuf + (size_t) view * frame;
+    const float4* __restrict__ xf = p.xf + (size_t) view * p.nuniq;
+    uint32_t* vflags = p.flags + view;
+    const float twm1 = gel::i2f(p.tw - 1), thm1 = gel::i2f(p.th - 1);
     const int nstrips = (rx1 - rx0 + 8) / 8;
     for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
@@ -597,7 +605,7 @@ direct_resolve_kernel(DirectParams p)
             const unsigned long long key = next_key;
             if(y + CTA_ROWS <= ry1) next_key = vkeys[off + CTA_ROWS];         /* one iteration ahead of its use */
             uint32_t colour; float z;
-            direct_shade<COMPACT>(p, view, key, x, y, colour, z);
+            direct_shade<COMPACT>(p, xf, vflags, twm1, thm1, key, x, y, colour, z);
             vkeys[off] = CLEAR_KEY;                                       /* the buffer is all "no winner" again for the next batch */
             vpixel[off] = colour;
             vz[off] = z;

@@ -29,7 +29,10 @@
 
 namespace gelk {
 
-constexpr int TW = 32;             /* tile width  (screen x, the framebuffer's SLOW axis)                */
+#ifndef GEL_TW
+#define GEL_TW 32
+#endif
+constexpr int TW = GEL_TW;         /* tile width  (screen x, the framebuffer's SLOW axis)                */
 constexpr int TH = 32;             /* tile height (screen y, contiguous in memory: index y + x*yres)     */
 #ifndef GEL_RASTER_THREADS
 #define GEL_RASTER_THREADS 128
@@ -46,12 +49,12 @@ constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 #define GEL_TWO_PHASE_MIN 8
 #endif
 constexpr int FRAG_MAX = GEL_FRAG_MAX;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
-constexpr int UNIT_WINDOW = 512;   /* column units (one bbox column of one triangle) staged per warp per pass */
+constexpr int UNIT_WINDOW = 256;   /* column units (one bbox column of one triangle) staged per warp per pass */
 constexpr int QCAP = 64;           /* survivor stack per warp: < 32 left over + one row of 32 lanes       */
 constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16 B each, global scratch)   */
 constexpr int TWO_PHASE_MIN = GEL_TWO_PHASE_MIN;  /* tiles with fewer entries are rasterised in one phase                */
 constexpr int MAX_BATCH = 256;     /* views per launch set (K3 keeps a per-view prefix in shared memory)  */
-constexpr int DEFER_MAX = 256;     /* large triangles per round left to the CTA-wide sweep                */
+constexpr int DEFER_MAX = 48;      /* large triangles per round left to the CTA-wide sweep (their setup records wait in shared memory) */
 constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
 constexpr int SEG_SLOTS = RASTER_THREADS;   /* segments staged per round (one per thread)                 */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
@@ -350,7 +353,8 @@ struct RasterSmem
     WarpScratch ws[RASTER_WARPS];
     int seg_first[SEG_SLOTS];
     int seg_pre[SEG_SLOTS];             /* exclusive prefix of the staged segment sizes */
-    int defer[DEFER_MAX];               /* entry-pool indices of triangles left to the CTA-wide sweep */
+    float4 dslab[4][DEFER_MAX];         /* setup records (q0..q3 of the slab layout) of the triangles left to the CTA-wide sweep */
+    uint32_t dbbox[DEFER_MAX];
     int view_pre[MAX_BATCH + 1];        /* exclusive prefix of the views' lit-tile counts */
     int chain[NCHAIN];
     int warp_sums[RASTER_WARPS];
@@ -448,14 +452,13 @@ __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws
 
 /* reset (main.c:413-417) of a tile no triangle touches: pure HBM stores, one warp per tile.  The rasteriser CTAs
  * issue these fire-and-forget stores between their work items, so they overlap the instruction-bound raster work. */
-/* stage 2 of the CTA-wide sweep: the survivor's triangle record lives in the scratch of the thread that set it up */
+/* stage 2 of the CTA-wide sweep: the survivor's triangle record is one of the deferred records */
 __device__ __forceinline__ void resolve_swept(RasterSmem& sm, WarpScratch& ws, int i)
 {
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
-    const WarpScratch& os = sm.ws[id >> 15];
-    const int src = (id >> 10) & 31;
-    const unsigned long long key = fragment_key(n.x, n.y, os.slab[2][src].w, os.slab[3][src]);
+    const int src = id >> 10;
+    const unsigned long long key = fragment_key(n.x, n.y, sm.dslab[2][src].w, sm.dslab[3][src]);
     unsigned long long* k = sm.keys + (id & 1023);
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
@@ -597,8 +600,15 @@ raster_kernel(RasterParams p)
                 bool unitised = r.npx > 0;
                 if(r.npx > FRAG_MAX)
                 {
+                    /* too large for the unit path: its record waits in shared memory for the CTA-wide sweep (no second
+                     * gather, no second setup); when the list is full the unit path takes it after all */
                     const int slot = atomicAdd(&sm.ndefer, 1);
-                    if(slot < DEFER_MAX) { sm.defer[slot] = (int) tri; unitised = false; }
+                    if(slot < DEFER_MAX)
+                    {
+                        sm.dslab[0][slot] = r.q0; sm.dslab[1][slot] = r.q1; sm.dslab[2][slot] = r.q2; sm.dslab[3][slot] = r.q3;
+                        sm.dbbox[slot] = r.bbox;
+                        unitised = false;
+                    }
                 }
                 if(unitised)
                 {
@@ -678,73 +688,59 @@ raster_kernel(RasterParams p)
         };
 
         /* large triangles: the whole CTA sweeps one triangle at a time in 4x8-pixel patches dealt to the warps;
-         * survivors of the cheap tests are compacted so the divisions run in full warps */
+         * survivors of the cheap tests are compacted so the divisions run in full warps.  Called after a barrier that
+         * makes the deferred records visible; ends with one. */
         auto sweep_deferred = [&]()
         {
             const int ndefer = min(sm.ndefer, DEFER_MAX);
-            for(int base = 0; base < ndefer; base += RASTER_THREADS)
+            int sq = 0;                                                   /* survivors on this warp's stack */
+            for(int li = 0; li < ndefer; li++)
             {
-                if(base + tid < ndefer)
+                const uint32_t bb = sm.dbbox[li];
+                const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
+                const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
+                const float4 q0 = sm.dslab[0][li], q1 = sm.dslab[1][li], q2 = sm.dslab[2][li];
+                const float den_hi = q2.w * U_SLACK;
+                /* the bbox is covered by patches of 4 columns x 8 rows (lane = 8*column + row): clipped bboxes are
+                 * rarely 32 rows tall, so this keeps far more lanes busy than one 32-row column per warp */
+                const int pcols = (gx1 - gx0 + 4) >> 2, prows = (gy1 - gy0 + 8) >> 3;
+                for(int pr = 0; pr < prows; pr++)
                 {
-                    const uint32_t tri = (uint32_t) sm.defer[base + tid];
-                    const float4 a = __ldg(xf + __ldg(p.i0 + tri)), b = __ldg(xf + __ldg(p.i1 + tri)), c = __ldg(xf + __ldg(p.i2 + tri));
-                    const TriRecord r = make_record(a, b, c, tri, px0, py0, px1, py1);
-                    ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
-                    ws.bbox[lane] = r.bbox;
-                }
-                __syncthreads();
-                const int cnt = min(RASTER_THREADS, ndefer - base);
-                int sq = 0;                                               /* survivors on this warp's stack */
-                for(int li = 0; li < cnt; li++)
-                {
-                    const WarpScratch& os = sm.ws[li >> 5];
-                    const int src = li & 31;
-                    const uint32_t bb = os.bbox[src];
-                    const int gx0 = bb & 31, gx1 = (bb >> 5) & 31, gy0 = (bb >> 10) & 31, gy1 = (bb >> 15) & 31;
-                    const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
-                    const float4 q0 = os.slab[0][src], q1 = os.slab[1][src], q2 = os.slab[2][src];
-                    const float den_hi = q2.w * U_SLACK;
-                    /* the bbox is covered by patches of 4 columns x 8 rows (lane = 8*column + row): clipped bboxes are
-                     * rarely 32 rows tall, so this keeps far more lanes busy than one 32-row column per warp */
-                    const int pcols = (gx1 - gx0 + 4) >> 2, prows = (gy1 - gy0 + 8) >> 3;
-                    for(int pr = 0; pr < prows; pr++)
+                    const int yl = gy0 + pr * 8 + (lane & 7);
+                    const bool rowok = yl <= gy1;
+                    const float v2y = gel::sub(gel::i2f(py0 + yl), q0.y);
+                    const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
+                    for(int pc = warp; pc < pcols; pc += RASTER_WARPS)
                     {
-                        const int yl = gy0 + pr * 8 + (lane & 7);
-                        const bool rowok = yl <= gy1;
-                        const float v2y = gel::sub(gel::i2f(py0 + yl), q0.y);
-                        const float cy0 = gel::mul(v2y, q0.w), cy1 = gel::mul(v2y, q1.y);
-                        for(int pc = warp; pc < pcols; pc += RASTER_WARPS)
+                        const int xl = gx0 + pc * 4 + (lane >> 3);
+                        const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
+                        const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
+                        const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
+                        const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                        const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                        const bool pass = rowok && xl <= gx1 && may_be_inside(nv, nw, eps, den_hi);
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                        if(pass)
                         {
-                            const int xl = gx0 + pc * 4 + (lane >> 3);
-                            const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
-                            const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), cy0), q1.z);
-                            const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), cy1), q1.w);
-                            const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
-                            const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
-                            const bool pass = rowok && xl <= gx1 && may_be_inside(nv, nw, eps, den_hi);
-                            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-                            if(pass)
-                            {
-                                const int slot = sq + __popc(m & lt_mask);
-                                ws.q_id[slot] = (uint32_t) li << 10 | (uint32_t) xl << 5 | (uint32_t) yl;
-                                ws.q_n[slot] = make_float2(nv, nw);
-                            }
-                            sq += __popc(m);
-                            if(sq >= 32)
-                            {
-                                /* divisions, inside test, depth, key for a full warp of survivors */
-                                __syncwarp();
-                                sq -= 32;
-                                resolve_swept(sm, ws, sq + lane);
-                                __syncwarp();
-                            }
+                            const int slot = sq + __popc(m & lt_mask);
+                            ws.q_id[slot] = (uint32_t) li << 10 | (uint32_t) xl << 5 | (uint32_t) yl;
+                            ws.q_n[slot] = make_float2(nv, nw);
+                        }
+                        sq += __popc(m);
+                        if(sq >= 32)
+                        {
+                            /* divisions, inside test, depth, key for a full warp of survivors */
+                            __syncwarp();
+                            sq -= 32;
+                            resolve_swept(sm, ws, sq + lane);
+                            __syncwarp();
                         }
                     }
                 }
-                __syncwarp();
-                if(lane < sq) resolve_swept(sm, ws, lane);
-                __syncthreads();
             }
+            __syncwarp();
+            if(lane < sq) resolve_swept(sm, ws, lane);
+            __syncthreads();
         };
 
         /* ---------------- phase 0: walk the tile's segments; near triangles are rasterised, far ones parked ---------------- */

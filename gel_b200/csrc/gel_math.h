@@ -209,6 +209,19 @@ GEL_HD void fragment_shade(float v, float w, float u, const float* uv, float sa,
     shading = trunc_i(mul(255.0f, clamped));
 }
 
+/* the same with (float) (tw - 1), (float) (th - 1) converted once by the caller (identical values) */
+GEL_HD void fragment_shade_f(float v, float w, float u, const float* uv, float sa, float sb, float sc,
+                             float twm1, float thm1, int& xx, int& yy, int& shading)
+{
+    const float s = add(add(mul(v, uv[2]), mul(w, uv[4])), mul(u, uv[0]));
+    const float t = add(add(mul(v, uv[3]), mul(w, uv[5])), mul(u, uv[1]));
+    xx = trunc_i(mul(twm1, add(0.0f, s)));
+    yy = trunc_i(mul(thm1, sub(1.0f, t)));
+    const float intensity = add(add(mul(v, sb), mul(w, sc)), mul(u, sa));
+    const float clamped = intensity < 0.0f ? 0.0f : intensity > 1.0f ? 1.0f : intensity;
+    shading = trunc_i(mul(255.0f, clamped));
+}
+
 /* pshade, main.c:334-340 */
 GEL_HD uint32_t pshade(uint32_t p, int shading)
 {

@@ -50,7 +50,7 @@ struct gelcu_ctx
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr, hi_stream = nullptr, aux_stream = nullptr;   /* side / hi: HBM-bound fill beside the raster kernels (hi = higher priority); aux: small result copies */
     cudaEvent_t side_go = nullptr, side_done = nullptr, stats_go = nullptr, stats_ready[2] = { nullptr, nullptr };
-    int fill_mode = 0, fill_ctas = 1, red_hint = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
+    int fill_mode = 0, fill_ctas = 1, red_hint = 0, fill_sleep_ns = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr; bool trec_compact = false, allow_compact = true;
@@ -222,8 +222,8 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             if(early_fill)
             {
                 const int grid = c->num_sms * std::max(1, std::min(c->fill_ctas, 8));
-                if(c->fill_mode == 1) { if(want_hash) direct_fill_persistent_kernel<true, true><<<grid, 256, 0, fs>>>(dp); else direct_fill_persistent_kernel<false, true><<<grid, 256, 0, fs>>>(dp); }
-                else { if(want_hash) direct_fill_persistent_kernel<true, false><<<grid, 256, 0, fs>>>(dp); else direct_fill_persistent_kernel<false, false><<<grid, 256, 0, fs>>>(dp); }
+                if(c->fill_mode == 1) { if(want_hash) direct_fill_persistent_kernel<true, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); else direct_fill_persistent_kernel<false, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); }
+                else { if(want_hash) direct_fill_persistent_kernel<true, false><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); else direct_fill_persistent_kernel<false, false><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); }
             }
             else
             {
@@ -596,6 +596,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_mode must be 0, 1 or 2"); c->fill_mode = value; }
     else if(!strcmp(name, "fill_ctas_per_sm")) { if(value < 1 || value > 8) return fail(GELCU_E_INVALID, "fill_ctas_per_sm out of [1,8]"); c->fill_ctas = value; }
     else if(!strcmp(name, "red_hint")) c->red_hint = value != 0;
+    else if(!strcmp(name, "fill_sleep_ns")) { if(value < 0 || value > 1000000) return fail(GELCU_E_INVALID, "fill_sleep_ns out of [0, 1000000]"); c->fill_sleep_ns = value; }
     else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
     return GELCU_OK;
