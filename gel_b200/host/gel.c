@@ -3,11 +3,14 @@
  *
  *   reference main()                          here
  *   ----------------------------------------  -------------------------------------------------------
- *   oload / oparse / tvgen / ttgen / tngen    gel_obj_load                        (gel_host.c)
+ *   oload / oparse                            gel_obj_parse                       (gel_host.c)
+ *   tvgen / ttgen / tngen                     gelcu_set_mesh_indexed: on the device (--soups: gel_obj_expand on the host
+ *                                             + gelcu_set_mesh, the reference's own three soups)
  *   sload                                     gel_bmp_load
  *   ssetup(800, 600)                          gelcu_create(device, xres, yres)    default 800x600, --res
  *   iinit / ipump (mouse)                     scripted input: --mouse DX,DY per frame, or --sweep N
- *   slock .. reset .. tdraw loop .. sunlock   gelcu_render(views...)
+ *   slock .. reset .. tdraw loop .. sunlock   gelcu_render(views...); --region: gelcu_render_region into reused frame slots
+ *                                             (only each view's screen region crosses PCIe)
  *   schurn / spresent                         per-frame JSON line (FNV-1a-64, non-zero pixels), optional
  *                                             raw dump (--dump) or upright PPM (--ppm); with --sink rgb8 the
  *                                             un-rotation + 24-bit pack happen on the device
@@ -31,8 +34,9 @@
 
 typedef struct
 {
-    int device, first, count, xres, yres, batch, readback, sink;
-    const GelMesh* mesh; const GelTexture* tex; const gelcu_view* views;
+    int device, first, count, xres, yres, batch, readback, sink, region;
+    const GelObj* obj; const GelMesh* mesh; const GelTexture* tex; const gelcu_view* views;
+    gelcu_rect* rects;       /* region mode: one per frame slot, carried from chunk to chunk */
     uint32_t* pixels;        /* count frames (readback); with sink: count upright 24-bit frames */
     uint64_t* hashes;        /* 2 per view */
     float device_ms; double wall_s; int rc; char err[512];
@@ -52,13 +56,16 @@ static void* shard_main(void* arg)
     Shard* s = (Shard*) arg;
     gelcu_ctx* ctx = NULL;
     s->rc = gelcu_create(&ctx, s->device, s->xres, s->yres);
-    if(s->rc == 0) s->rc = gelcu_set_mesh(ctx, s->mesh->tv, s->mesh->tn, s->mesh->tt, s->mesh->ntri);
+    if(s->rc == 0)
+        s->rc = s->mesh ? gelcu_set_mesh(ctx, s->mesh->tv, s->mesh->tn, s->mesh->tt, s->mesh->ntri)
+                        : gelcu_set_mesh_indexed(ctx, s->obj->v, s->obj->nv, s->obj->vt, s->obj->nvt, s->obj->vn, s->obj->nvn, s->obj->faces, s->obj->nfaces);
     if(s->rc == 0) s->rc = gelcu_set_texture(ctx, s->tex->pixels, s->tex->w, s->tex->h);
     if(s->rc == 0 && s->batch > 0) s->rc = gelcu_set_option(ctx, "batch_views", s->batch);
     if(s->rc == 0)
     {
         const double t0 = now_s();
-        if(s->sink && s->readback) s->rc = gelcu_render_rgb8(ctx, s->views + s->first, s->count, (uint8_t*) s->pixels, s->hashes, &s->device_ms);
+        if(s->region && s->readback) s->rc = gelcu_render_region(ctx, s->views + s->first, s->count, s->pixels, NULL, s->rects, s->sink, s->hashes, &s->device_ms);
+        else if(s->sink && s->readback) s->rc = gelcu_render_rgb8(ctx, s->views + s->first, s->count, (uint8_t*) s->pixels, s->hashes, &s->device_ms);
         else s->rc = gelcu_render(ctx, s->views + s->first, s->count, s->readback ? s->pixels : NULL, NULL, s->hashes, &s->device_ms);
         s->wall_s = now_s() - t0;
         gelcu_get_stats(ctx, &s->stats);
@@ -71,7 +78,7 @@ static void* shard_main(void* arg)
 int main(int argc, char* argv[])
 {
     const char* positional[2] = { NULL, NULL };
-    int npos = 0, xres = 800, yres = 600, frames = 1, dx = 0, dy = 0, sweep = 0, gpus = 1, batch = 0, readback = 1, sink = 0;
+    int npos = 0, xres = 800, yres = 600, frames = 1, dx = 0, dy = 0, sweep = 0, gpus = 1, batch = 0, readback = 1, sink = 0, region = 0, soups = 0;
     const char* dump_path = NULL; const char* ppm_prefix = NULL;
     for(int i = 1; i < argc; i++)
     {
@@ -84,6 +91,8 @@ int main(int argc, char* argv[])
         else if(!strcmp(argv[i], "--dump") && i + 1 < argc) dump_path = argv[++i];
         else if(!strcmp(argv[i], "--ppm") && i + 1 < argc) ppm_prefix = argv[++i];
         else if(!strcmp(argv[i], "--no-readback")) readback = 0;
+        else if(!strcmp(argv[i], "--region")) region = 1;
+        else if(!strcmp(argv[i], "--soups")) soups = 1;
         else if(!strcmp(argv[i], "--sink") && i + 1 < argc) { if(!strcmp(argv[++i], "rgb8")) sink = 1; else npos = 99; }
         else if(argv[i][0] == '-' && argv[i][1] == '-') npos = 99;
         else if(npos < 2) positional[npos++] = argv[i];
@@ -93,12 +102,14 @@ int main(int argc, char* argv[])
     {
         puts("args: path/to/obj path/to/bmp");
         puts("      [--res WxH] [--frames N] [--mouse DX,DY] [--sweep N] [--gpus G] [--batch B]");
-        puts("      [--dump frames.raw] [--ppm prefix] [--no-readback] [--sink rgb8]");
+        puts("      [--dump frames.raw] [--ppm prefix] [--no-readback] [--sink rgb8] [--region] [--soups]");
         return 1;
     }
-    GelMesh mesh; GelTexture tex;
-    int rc = gel_obj_load(positional[0], &mesh);
+    GelObj obj; GelMesh mesh; GelTexture tex;
+    memset(&mesh, 0, sizeof mesh);
+    int rc = gel_obj_parse(positional[0], &obj);
     if(rc == -1) { printf("could not open %s\n", positional[0]); exit(1); }
+    if(rc == 0 && soups) rc = gel_obj_expand(&obj, &mesh);              /* the reference's host-side tvgen / ttgen / tngen */
     if(rc != 0) { printf("could not parse %s (error %d)\n", positional[0], rc); exit(1); }
     rc = gel_bmp_load(positional[1], &tex);
     if(rc != 0) { printf("could not load %s (error %d; need an uncompressed 8-, 24- or 32-bit BMP)\n", positional[1], rc); exit(1); }
@@ -125,6 +136,13 @@ int main(int argc, char* argv[])
     /* frames come back in chunks so that long sweeps do not need nviews frames of host memory */
     const int chunk = readback ? (int) (((size_t) 1 << 30) / frame_bytes > 0 ? ((size_t) 1 << 30) / frame_bytes : 1) : nviews;
     uint64_t* hashes = (uint64_t*) calloc((size_t) 2 * nviews, sizeof(uint64_t));
+    /* frame slots: one allocation reused by every chunk (with --region the slots carry their rectangles from chunk to chunk,
+     * so a slot is only reset where the previous view drew and the new one does not) */
+    const int slots = nviews < chunk * gpus ? nviews : chunk * gpus;
+    uint32_t* pixels = NULL;
+    gelcu_rect* rects = (gelcu_rect*) calloc((size_t) slots, sizeof(gelcu_rect));
+    if(readback && gelcu_host_alloc((void**) &pixels, frame_bytes * (size_t) slots) != 0) { printf("host alloc failed: %s\n", gelcu_last_error()); exit(1); }
+    if(readback && region) { memset(pixels, 0, frame_bytes * (size_t) slots); for(int k = 0; k < slots; k++) { rects[k].x0 = 0; rects[k].y0 = 0; rects[k].x1 = -1; rects[k].y1 = -1; } }
     double dev_ms_max_sum = 0.0, wall_sum = 0.0;
     uint64_t launches = 0;
     int status = 0;
@@ -133,12 +151,10 @@ int main(int argc, char* argv[])
         const int n = nviews - base < chunk * gpus ? nviews - base : chunk * gpus;
         Shard shards[64]; pthread_t th[64];
         const int g_used = gpus > 64 ? 64 : gpus;
-        uint32_t* pixels = NULL;
-        if(readback && gelcu_host_alloc((void**) &pixels, frame_bytes * (size_t) n) != 0) { printf("host alloc failed: %s\n", gelcu_last_error()); exit(1); }
         for(int g = 0; g < g_used; g++)
         {
             const int lo = (int) ((long long) n * g / g_used), hi = (int) ((long long) n * (g + 1) / g_used);
-            Shard s = { g, base + lo, hi - lo, xres, yres, batch, readback, sink, &mesh, &tex, views,
+            Shard s = { g, base + lo, hi - lo, xres, yres, batch, readback, sink, region, &obj, soups ? &mesh : NULL, &tex, views, rects + lo,
                         readback ? (uint32_t*) ((uint8_t*) pixels + frame_bytes * lo) : NULL, hashes + 2 * (size_t) (base + lo), 0.0f, 0.0, 0, "", { 0 } };
             shards[g] = s;
             pthread_create(&th[g], NULL, shard_main, &shards[g]);
@@ -193,16 +209,17 @@ int main(int argc, char* argv[])
                 printf("{\"frame\": %d, \"checksum\": \"%016llx\", \"zchecksum\": \"%016llx\"}\n", base + k,
                        (unsigned long long) hashes[2 * (size_t) (base + k)], (unsigned long long) hashes[2 * (size_t) (base + k) + 1]);
         }
-        gelcu_host_free(pixels);
     }
+    gelcu_host_free(pixels);
+    free(rects);
     if(dump) fclose(dump);
     printf("{\"summary\": true, \"views\": %d, \"triangles\": %d, \"res\": \"%dx%d\", \"gpus\": %d, \"device_ms\": %.4f, "
            "\"frames_per_s_device\": %.2f, \"mtri_per_s_device\": %.3f, \"wall_s\": %.4f, \"gpu_launches\": %llu}\n",
-           nviews, mesh.ntri, xres, yres, gpus, dev_ms_max_sum,
+           nviews, obj.nfaces, xres, yres, gpus, dev_ms_max_sum,
            dev_ms_max_sum > 0 ? nviews / (dev_ms_max_sum * 1e-3) : 0.0,
-           dev_ms_max_sum > 0 ? (double) mesh.ntri * nviews / (dev_ms_max_sum * 1e-3) / 1e6 : 0.0, wall_sum,
+           dev_ms_max_sum > 0 ? (double) obj.nfaces * nviews / (dev_ms_max_sum * 1e-3) / 1e6 : 0.0, wall_sum,
            (unsigned long long) launches);
     free(hashes); free(views);
-    gel_mesh_free(&mesh); gel_texture_free(&tex);
+    gel_mesh_free(&mesh); gel_obj_free(&obj); gel_texture_free(&tex);
     return status;
 }

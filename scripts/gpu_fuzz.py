@@ -80,6 +80,28 @@ def main():
                         print(f"seed {seed} pipeline {pl} rep {rep} res {res} tris {tv.shape[0]}: MISMATCH pixels {(out['pixel'] != ref['pixel']).sum()} "
                               f"z {(out['z'].view(np.uint32) != ref['z'].view(np.uint32)).sum()} rc {out['rc']} clipped {ref['clipped']}")
                         break
+                # region output into frame slots that hold garbage / another view's frame, with "anything" or stale rectangles
+                nv = len(bases); W, H = res
+                frames = rng.integers(0, 1 << 32, (nv, W * H), dtype=np.uint32); zs = rng.uniform(-1, 1, (nv, W * H)).astype(np.float32)
+                rects = np.tile(np.array([0, 0, W - 1, H - 1], np.int32), (nv, 1))
+                for order in (np.arange(nv), np.arange(nv)[::-1].copy()):
+                    out = r.render_region(bases[order], frames, rects, z_io=zs, hashes=True)
+                    if not (np.array_equal(frames, ref["pixel"][order]) and np.array_equal(zs.view(np.uint32), ref["z"][order].view(np.uint32))
+                            and np.array_equal(out["hash"], ref["hash"][order])):
+                        bad += 1
+                        print(f"seed {seed} pipeline {pl} res {res}: REGION MISMATCH pixels {(frames != ref['pixel'][order]).sum()}"); break
+                # the same scene through the indexed entry: corners become (position, normal) index pairs of a random small vertex pool
+                if pl == 1 and seed % 3 == 0:
+                    pv, inv = np.unique(tv.reshape(-1, 3), axis=0, return_inverse=True)
+                    pn, inn = np.unique(tn.reshape(-1, 3), axis=0, return_inverse=True)
+                    pt, itt = np.unique(tt.reshape(-1, 3), axis=0, return_inverse=True)
+                    scale = np.float32(int(np.sqrt((pv.astype(np.float32) ** 2).sum(1, dtype=np.float32)).max())) if len(pv) else np.float32(0)
+                    if scale == 1:                                           # (int) max|v| == 1: the scaled positions are the positions
+                        faces = np.concatenate([inv.reshape(-1, 3), itt.reshape(-1, 3), inn.reshape(-1, 3)], 1).astype(np.int32)
+                        r.set_mesh_indexed(pv, pt, pn, faces)
+                        out = r.render(bases, z=True, hashes=True)
+                        if not (np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(out["hash"], ref["hash"])):
+                            bad += 1; print(f"seed {seed} res {res}: INDEXED MISMATCH pixels {(out['pixel'] != ref['pixel']).sum()}")
     print(f"fuzz: {seeds} seeds x 2 pipelines x 2 calls, {bad} failures, {time.time() - t0:.0f} s")
     return 1 if bad else 0
 

@@ -25,7 +25,23 @@ for pl in (1, 2):
         up = ref["pixel"][0].reshape(W, H).T[::-1]                           # frame sink: upright 24-bit frames
         rgb = r.render_rgb8(bases)["rgb"]
         assert np.array_equal(rgb[0], np.stack([(up >> 16) & 255, (up >> 8) & 255, up & 255], -1).astype(np.uint8)), (pl, W, H, "sink")
+        # round 2 entry points: region output into reused slots (sideways + rgb8), indexed mesh (device soup generation),
+        # the persistent overlapped fill with cache hints
+        frames = np.zeros((3, W * H), np.uint32); rects = np.tile(np.array([0, 0, -1, -1], np.int32), (3, 1))
+        r.render_region(bases, frames, rects, hashes=True)
+        assert np.array_equal(frames, ref["pixel"]), (pl, W, H, "region")
+        r.render_region(bases[::-1], frames, rects)
+        assert np.array_equal(frames, ref["pixel"][::-1]), (pl, W, H, "region, second call")
+        r.set_option("fill_mode", 1); r.set_option("red_hint", 1)
+        out = r.render(bases, z=True, hashes=True)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(out["hash"], ref["hash"]), (pl, W, H, "fill_mode 1")
         r.close()
+v, vt, vn, faces = gel_b200.load_obj_indexed(td + "/s.obj")
+r = gel_b200.Renderer(320, 240); r.set_mesh_indexed(v, vt, vn, faces); r.set_texture(tex)
+bases = gel_b200.view_bases([(0, 0), (0.4, 0.1)])
+ref = oracle.render_views(tv, tn, tt, tex, 320, 240, bases, nthreads=2, hashes=True)
+assert np.array_equal(r.render(bases, hashes=True)["hash"], ref["hash"]), "indexed"
+r.close()
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck initcheck; do

@@ -593,6 +593,23 @@ def test_headless_gel_ppm_through_the_device_sink(cfg1_paths, tmp_path):
         assert host == dev and host.startswith(b"P6\n320 200\n255\n") and len(host) == 15 + 320 * 200 * 3
 
 
+def test_headless_gel_indexed_soups_and_region_agree(cfg1_paths, tmp_path):
+    """`gel` loads through gelcu_set_mesh_indexed by default (soups generated on the device); --soups takes the reference's
+    host-side tvgen / ttgen / tngen + gelcu_set_mesh; --region returns frames through gelcu_render_region into reused slots.
+    All three must print the same per-frame lines and dump the same frames."""
+    import json, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "gel_b200", "host", "gel")
+    common = [exe, *cfg1_paths, "--res", "400x304", "--sweep", "12", "--batch", "5"]
+    outs = {}
+    for name, extra in (("indexed", []), ("soups", ["--soups"]), ("region", ["--region"]), ("region_rgb8", ["--region", "--sink", "rgb8"]), ("rgb8", ["--sink", "rgb8"])):
+        dump = tmp_path / f"{name}.raw"
+        o = subprocess.run([*common, *extra, "--dump", str(dump)], capture_output=True, text=True, check=True).stdout
+        outs[name] = ([json.loads(l) for l in o.splitlines() if l.startswith("{") and "summary" not in l], dump.read_bytes())
+    assert outs["indexed"] == outs["soups"] == outs["region"] and len(outs["indexed"][0]) == 12
+    assert outs["region_rgb8"] == outs["rgb8"]
+
+
 def test_differential_fuzz_sample(monkeypatch):
     """A slice of scripts/gpu_fuzz.py (adversarial random scenes: slivers, sub-pixel and screen-filling triangles,
     duplicates, coplanar stacks, off-screen and out-of-texture inputs; both pipelines, two calls per context)."""
