@@ -44,6 +44,9 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #ifndef GEL_DIRECT_TPW
 #define GEL_DIRECT_TPW 1024
 #endif
+#ifndef GEL_TRIM_ROUNDS
+#define GEL_TRIM_ROUNDS 1          /* rounds of exact bbox trimming per rasterised triangle (0 = off) */
+#endif
 constexpr int RESOLVE_WCOLS = GEL_RESOLVE_WCOLS;
 constexpr int TREC_QUADS = 4;                    /* wide static record per triangle for the resolve pass: 64 bytes */
 constexpr int TREC_COMPACT_BITS = 21;            /* meshes with < 2^21 distinct vertices: 32-byte record, three 21-bit indices */
@@ -313,16 +316,25 @@ direct_raster_kernel(DirectParams p)
             {
                 const bool guard = ad <= GUARD_DEN_MAX;
                 const float sg = s.den < 0.0f ? -1.0f : 1.0f;
-                ws.slab[0][lane] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
-                ws.slab[1][lane] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
-                ws.slab[2][lane] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
-                ws.slab[3][lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
-                ws.bx[lane] = (uint32_t) x0 | (uint32_t) x1 << 16;
-                ws.by[lane] = (uint32_t) y0 | (uint32_t) y1 << 13 | (guard ? 1u << 26 : 0u);
-                ws.den_hi[lane] = s.den * sg * U_SLACK;
-                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-                sweep = bh > DIRECT_MAX_ROWS || bw * bh > FRAG_MAX;
-                if(!sweep) { nun = bw; ux = x0; }
+                const float4 q2 = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
+                /* edges of the bbox on which no pixel can pass main.c:352 are dropped before any pixel is tested (exact:
+                 * gel_math.h, bbox_trim); a tiny triangle's first column and first row almost always go */
+                #pragma unroll
+                for(int round = 0; round < GEL_TRIM_ROUNDS; round++)
+                    gel::bbox_trim(s.ax, s.ay, s.v0x, s.v0y, s.v1x, s.v1y, s.k0, s.k1, q2.x, q2.y, q2.z, q2.w, x0, y0, x1, y1);
+                if(x0 <= x1 && y0 <= y1)
+                {
+                    ws.slab[0][lane] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
+                    ws.slab[1][lane] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
+                    ws.slab[2][lane] = q2;
+                    ws.slab[3][lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
+                    ws.bx[lane] = (uint32_t) x0 | (uint32_t) x1 << 16;
+                    ws.by[lane] = (uint32_t) y0 | (uint32_t) y1 << 13 | (guard ? 1u << 26 : 0u);
+                    ws.den_hi[lane] = s.den * sg * U_SLACK;
+                    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+                    sweep = bh > DIRECT_MAX_ROWS || bw * bh > FRAG_MAX;
+                    if(!sweep) { nun = bw; ux = x0; }
+                }
             }
         }
         __syncwarp();

@@ -174,6 +174,61 @@ GEL_HD float sign_guard(float den)
 }
 GEL_HD bool surely_negative(float num, float sden) { return mul(num, sden) < -1e-20f; }
 
+/* Exact bbox trimming.
+ *
+ * The reference tests every pixel of a triangle's bounding box (main.c:348-352), and a bbox of a small triangle is mostly
+ * empty: its first column x0 = trunc(min x) and first row lie left of / below every vertex.  bbox_trim removes an EDGE
+ * (first / last column, first / last row) of the box when every pixel on it provably fails the reference's inside test, so
+ * skipping those pixels cannot change a frame.  "Provably" means the kernels' own exact rejection (may_be_inside):
+ *     nv < -1e-20 (den <= 1e18)  =>  v < 0        nw likewise  =>  w < 0        nv + nw > den (1 + 1e-5)  =>  u < 0
+ * with  nv = fl(fl(A d20) - fl(C d21)),  nw = fl(fl(B d21) - fl(C d20)),  d20 = fl(fl(fl(v2x v0x) + fl(v2y v0y)) + k0)  etc.
+ * (A, B, C, D = d11, d00, d01, den after sign normalisation, v2x = fl(x - ax), v2y = fl(y - ay)).
+ *
+ * Proof.  Let NV(x, y) = A (X v0x + Y v0y + k0) - C (X v1x + Y v1y + k1), X = x - ax, Y = y - ay, in REAL arithmetic on the
+ * same float constants; likewise NW and S = NV + NW.  They are affine in (x, y), so on a segment they are bounded by their
+ * end-point values.  Standard forward error analysis of the float expressions (each operation: fl(t) = t (1 + e),
+ * |e| <= u = 2^-24) gives, for every pixel of the box,
+ *     |nv - NV| <= 7u (|A| M20 + |C| M21)      |nw - NW| <= 7u (|B| M21 + |C| M20)      |fl(nv + nw) - S| <= 8u (sum of both)
+ * with M20 = max|X| |v0x| + max|Y| |v0y| + |k0| (maxima over the box: attained at its corners), M21 likewise.  Hence for a
+ * pixel p on the segment [e1, e2]:  nv(p) <= NV(p) + E <= max(NV(e1), NV(e2)) + E <= max(nv(e1), nv(e2)) + 2E,  and if that is
+ * < -1e-20 every pixel of the segment has nv < -1e-20 and is rejected; the same for nw, and with min / > den_hi for the sum.
+ * E is taken as 32u (...) -- four times the bound -- plus 1e-24, which also covers the rounding of E's own evaluation and
+ * multiplications that underflow (only applied when (|A| + |C|)(M20 + M21)-like magnitudes that bound every intermediate are <= 1e30 -- no overflow --
+ * and |A| + |B| + |C| <= 1e12, so errors of underflowing products stay below 1e-30).  Any NaN makes every comparison false: nothing is trimmed.  The four corner values are
+ * evaluated with the kernels' operation order (not required by the proof).  Soundness is also checked by brute force on the
+ * host (tests/test_emu_math.py: every trimmed pixel is evaluated the reference's way). */
+GEL_HD void bbox_trim(float ax, float ay, float v0x, float v0y, float v1x, float v1y, float k0, float k1,
+                      float B /* d00 */, float C /* d01 */, float A /* d11 */, float D /* den, > 0 */,
+                      int& x0, int& y0, int& x1, int& y1)
+{
+    if(x0 > x1 || y0 > y1) return;
+    const float eps = D <= 1e18f ? -1e-20f : -INFINITY;
+    const float den_hi = mul(D, 1.00001f);
+    const float xa = sub(i2f(x0), ax), xb = sub(i2f(x1), ax), ya = sub(i2f(y0), ay), yb = sub(i2f(y1), ay);
+    const float xa0 = mul(xa, v0x), xa1 = mul(xa, v1x), xb0 = mul(xb, v0x), xb1 = mul(xb, v1x);
+    const float ya0 = mul(ya, v0y), ya1 = mul(ya, v1y), yb0 = mul(yb, v0y), yb1 = mul(yb, v1y);
+    float nv[4], nw[4], sm[4];                                         /* corners (x0,y0) (x0,y1) (x1,y0) (x1,y1) */
+    #define GEL_CORNER(k, cx0, cx1, cy0, cy1) { const float d20 = add(add(cx0, cy0), k0), d21 = add(add(cx1, cy1), k1); \
+        nv[k] = sub(mul(A, d20), mul(C, d21)); nw[k] = sub(mul(B, d21), mul(C, d20)); sm[k] = add(nv[k], nw[k]); }
+    GEL_CORNER(0, xa0, xa1, ya0, ya1) GEL_CORNER(1, xa0, xa1, yb0, yb1) GEL_CORNER(2, xb0, xb1, ya0, ya1) GEL_CORNER(3, xb0, xb1, yb0, yb1)
+    #undef GEL_CORNER
+    const float mx = fmaxf(fabsf(xa), fabsf(xb)), my = fmaxf(fabsf(ya), fabsf(yb));
+    const float m20 = add(add(mul(mx, fabsf(v0x)), mul(my, fabsf(v0y))), fabsf(k0));
+    const float m21 = add(add(mul(mx, fabsf(v1x)), mul(my, fabsf(v1y))), fabsf(k1));
+    const float tv_mag = add(mul(fabsf(A), m20), mul(fabsf(C), m21)), tw_mag = add(mul(fabsf(B), m21), mul(fabsf(C), m20));
+    /* guards, NaN-proof (a NaN makes the sums NaN and the comparisons false): the magnitudes that bound every intermediate
+     * of the corner evaluations are far from overflow, and the Gram terms small enough for underflow errors to vanish */
+    if(!(add(tv_mag, tw_mag) <= 1e30f) || !(add(add(fabsf(A), fabsf(B)), fabsf(C)) <= 1e12f) || !(D > 0.0f)) return;
+    const float u64 = 3.814697265625e-06f;                               /* 64 u = 2 x 32 u: the "2E" of the proof */
+    const float ev2 = add(mul(u64, tv_mag), 1e-24f), ew2 = add(mul(u64, tw_mag), 1e-24f);
+    const float tv = sub(eps, ev2), tw = sub(eps, ew2), ts = add(den_hi, add(ev2, ew2));
+    /* edge (i, j) is empty when one of the three conditions holds at both of its corners, with the slack */
+    #define GEL_EDGE(i, j) (fmaxf(nv[i], nv[j]) < tv || fmaxf(nw[i], nw[j]) < tw || fminf(sm[i], sm[j]) > ts)
+    const bool left = GEL_EDGE(0, 1), right = GEL_EDGE(2, 3), bottom = GEL_EDGE(0, 2), top = GEL_EDGE(1, 3);
+    #undef GEL_EDGE
+    x0 += left ? 1 : 0; x1 -= right ? 1 : 0; y0 += bottom ? 1 : 0; y1 -= top ? 1 : 0;
+}
+
 /* Orderable 32-bit key of a float: a > b  <=>  zkey(a) > zkey(b) for all non-NaN a != b (and +0 > -0). */
 GEL_HD uint32_t zkey(float z)
 {

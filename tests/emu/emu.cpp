@@ -18,7 +18,7 @@ extern "C" void emu_transform(const float* tv, const float* tn, int ntri, const 
 }
 
 extern "C" int emu_render(const float* tv, const float* tn, const float* tt, int ntri, const uint32_t* tex, int tw, int th,
-                          int xres, int yres, const float* basis, uint32_t* pixel, float* zbuff, int use_sign_guard)
+                          int xres, int yres, const float* basis, uint32_t* pixel, float* zbuff, int use_sign_guard, int trim_rounds)
 {
     const uint64_t CLEAR = (0x00800000ull << 32) | 0xFFFFFFFFull;
     std::vector<float> vew(9 * (size_t) ntri), shade(3 * (size_t) ntri);
@@ -32,6 +32,12 @@ extern "C" int emu_render(const float* tv, const float* tn, const float* tt, int
         int x0 = s.x0, y0 = s.y0, x1 = s.x1, y1 = s.y1;
         if(x0 < 0 || y0 < 0 || x1 > xres - 1 || y1 > yres - 1) { flags |= 1; if(x0 < 0) x0 = 0; if(y0 < 0) y0 = 0; if(x1 > xres - 1) x1 = xres - 1; if(y1 > yres - 1) y1 = yres - 1; }
         const float sden = use_sign_guard ? gel::sign_guard(s.den) : 0.0f;
+        if(fabsf(s.den) > 0.0f)                                           /* the kernels' exact bbox trimming, on the sign-normalised terms */
+        {
+            const float sg = s.den < 0.0f ? -1.0f : 1.0f;
+            for(int round = 0; round < trim_rounds; round++)
+                gel::bbox_trim(s.ax, s.ay, s.v0x, s.v0y, s.v1x, s.v1y, s.k0, s.k1, s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg, x0, y0, x1, y1);
+        }
         for(int x = x0; x <= x1; x++)
             for(int y = y0; y <= y1; y++)
             {
@@ -75,4 +81,37 @@ extern "C" uint64_t emu_salted_sum(const uint32_t* w, uint64_t n)
     uint64_t s = 0;
     for(uint64_t i = 0; i < n; i++) s += gel::salt_mix(w[i], (uint32_t) i);
     return s;
+}
+
+
+/* Brute-force soundness of bbox_trim: for every triangle (9 screen-space floats) every pixel of its clipped bbox that the
+ * trimming removes is evaluated the reference's way (tbarycenter, main.c:316-332, 352); returns how many of them are inside
+ * (must be 0).  counts[0] += bbox pixels, counts[1] += pixels left after trimming, counts[2] += pixels inside. */
+extern "C" uint64_t emu_trim_soundness(const float* vew, int ntri, int xres, int yres, int rounds, uint64_t* counts)
+{
+    uint64_t wrong = 0;
+    for(int t = 0; t < ntri; t++)
+    {
+        const float* p = vew + 9 * (size_t) t;
+        const gel::TriSetup s = gel::tri_setup(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+        int x0 = s.x0 < 0 ? 0 : s.x0, y0 = s.y0 < 0 ? 0 : s.y0, x1 = s.x1 > xres - 1 ? xres - 1 : s.x1, y1 = s.y1 > yres - 1 ? yres - 1 : s.y1;
+        if(x0 > x1 || y0 > y1 || !(fabsf(s.den) > 0.0f)) continue;
+        int tx0 = x0, ty0 = y0, tx1 = x1, ty1 = y1;
+        const float sg = s.den < 0.0f ? -1.0f : 1.0f;
+        for(int round = 0; round < rounds; round++)
+            gel::bbox_trim(s.ax, s.ay, s.v0x, s.v0y, s.v1x, s.v1y, s.k0, s.k1, s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg, tx0, ty0, tx1, ty1);
+        counts[0] += (uint64_t) (x1 - x0 + 1) * (uint64_t) (y1 - y0 + 1);
+        if(tx0 <= tx1 && ty0 <= ty1) counts[1] += (uint64_t) (tx1 - tx0 + 1) * (uint64_t) (ty1 - ty0 + 1);
+        for(int x = x0; x <= x1; x++)
+            for(int y = y0; y <= y1; y++)
+            {
+                float nv, nw, v, w, u, z;
+                gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
+                const bool inside = gel::bary_inside(s, nv, nw, v, w, u, z);
+                counts[2] += inside;
+                const bool kept = x >= tx0 && x <= tx1 && y >= ty0 && y <= ty1;
+                if(inside && !kept) wrong++;
+            }
+    }
+    return wrong;
 }

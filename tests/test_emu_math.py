@@ -18,13 +18,13 @@ def emu():
     return ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libgelemu.so"))
 
 
-def emu_render(E, tv, tn, tt, tex, xres, yres, basis, guard=1):
+def emu_render(E, tv, tn, tt, tex, xres, yres, basis, guard=1, trim=2):
     px, zb = np.empty(xres * yres, np.uint32), np.empty(xres * yres, np.float32)
     tv, tn, tt = (np.ascontiguousarray(a, np.float32) for a in (tv, tn, tt))
     tex = np.ascontiguousarray(tex, np.uint32)
     f = E.emu_render(tv.ctypes.data_as(_fp), tn.ctypes.data_as(_fp), tt.ctypes.data_as(_fp), tv.shape[0], tex.ctypes.data_as(_up),
                      tex.shape[1], tex.shape[0], xres, yres, np.ascontiguousarray(basis, np.float32).ctypes.data_as(_fp),
-                     px.ctypes.data_as(_up), zb.ctypes.data_as(_fp), guard)
+                     px.ctypes.data_as(_up), zb.ctypes.data_as(_fp), guard, trim)
     return px, zb, f
 
 
@@ -72,3 +72,56 @@ def test_salted_sum_definition(emu):
     w = np.random.default_rng(5).integers(0, 2**32, 5000, dtype=np.uint32)
     emu.emu_salted_sum.restype = ctypes.c_uint64
     assert emu.emu_salted_sum(w.ctypes.data_as(_up), ctypes.c_uint64(w.size)) == oracle.salted_sum(w)
+
+
+def _adversarial_triangles(rng, n, res):
+    """Screen-space triangles built to stress bbox_trim: vertices on / next to integer pixel coordinates (the first column and row
+    of the bbox then touch the triangle), slivers, sub-pixel and 40-pixel triangles, flat and steep in z (the reference's
+    barycentrics use the 3-D Gram matrix, so a steep triangle's coverage is sheared against its 2-D outline)."""
+    c = np.stack([rng.uniform(2, res[0] - 3, n), rng.uniform(2, res[1] - 3, n)], 1)
+    size = np.exp(rng.uniform(np.log(0.05), np.log(40.0), n))[:, None, None]
+    xy = c[:, None, :] + rng.uniform(-1, 1, (n, 3, 2)) * size
+    snap = rng.integers(0, 4, (n, 3, 2))                                   # 0 free, 1 exactly integer, 2 integer +- 1 ulp-ish, 3 integer +- 1e-3
+    r = np.rint(xy)
+    xy = np.where(snap == 1, r, xy)
+    xy = np.where(snap == 2, r + rng.choice([-1, 1], (n, 3, 2)) * r * 6e-8, xy)
+    xy = np.where(snap == 3, r + rng.uniform(-1e-3, 1e-3, (n, 3, 2)), xy)
+    sliver = rng.random(n) < 0.2
+    t = rng.uniform(-0.5, 1.5, n)[:, None]
+    xy[sliver, 2] = xy[sliver, 0] + (xy[sliver, 1] - xy[sliver, 0]) * t[sliver] + rng.normal(0, 1e-3, (int(sliver.sum()), 2))
+    zscale = np.exp(rng.uniform(np.log(1e-4), np.log(30.0), n))[:, None]
+    z = 0.5 + rng.uniform(-1, 1, (n, 3)) * zscale
+    xy = np.clip(xy, 0.0, np.array([res[0] - 1.001, res[1] - 1.001]))
+    return np.concatenate([xy, z[:, :, None]], 2).astype(np.float32).reshape(n, 9)
+
+
+@pytest.mark.parametrize("res", [(8192, 8192), (640, 480)])
+def test_bbox_trim_never_removes_an_inside_pixel(emu, res):
+    """Brute force: every pixel that bbox_trim (gel_math.h) removes from a triangle's bbox is evaluated the reference's way
+    (tbarycenter + the >= 0 test, main.c:316-332,352) -- none may be inside.  1.5 M adversarial triangles per resolution,
+    one and three rounds of trimming; and the trimming must actually remove a large share of the box."""
+    emu.emu_trim_soundness.restype = ctypes.c_uint64
+    rng = np.random.default_rng(res[0])
+    tri = _adversarial_triangles(rng, 1_500_000, res)
+    for rounds in (1, 3):
+        counts = (ctypes.c_uint64 * 3)(0, 0, 0)
+        wrong = emu.emu_trim_soundness(tri.ctypes.data_as(_fp), tri.shape[0], res[0], res[1], rounds, counts)
+        assert wrong == 0, f"{wrong} inside pixels were trimmed away ({rounds} rounds)"
+        assert counts[2] > 1_000_000 and counts[1] < 0.96 * counts[0]       # real coverage, real trimming (large triangles dominate the count here)
+
+
+def test_bbox_trim_on_the_cfg3_sphere(emu):
+    """The workload it is meant for: one view of the 1 M-triangle sphere at 4K -- nothing inside is trimmed, and most of the tested
+    pixels go (the figure quoted in DESIGN.md)."""
+    from gel_b200 import synth
+    import gel_b200, tempfile
+    emu.emu_trim_soundness.restype = ctypes.c_uint64
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "s.obj")
+        open(obj, "w").write(synth.sphere_obj_text(200, 200))                  # 80 000 triangles: the cfg-3 geometry at 1/12 of the count
+        tv, tn, _ = gel_b200.load_obj(obj)
+    vew, _ = oracle.transform(tv, tn, oracle.view_basis(0.49, 0.0), 1100, 620)   # same pixels-per-triangle as 707 x 707 at 3840 x 2160
+    for rounds, most in ((1, 0.75), (2, 0.6)):
+        counts = (ctypes.c_uint64 * 3)(0, 0, 0)
+        assert emu.emu_trim_soundness(vew.ctypes.data_as(_fp), vew.shape[0], 1100, 620, rounds, counts) == 0
+        assert counts[1] < most * counts[0]
