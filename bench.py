@@ -252,8 +252,8 @@ def recorded_traffic(kernel: str, name: str):
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except (OSError, ValueError):
         return None, "no profiles/traffic.json"
-    rec = tj.get(kernel)
-    if not rec or rec.get("workload") != name:
+    rec = next((r for r in tj.get("records", []) if r.get("kernel") == kernel and r.get("workload") == name), None)
+    if rec is None:
         return None, "no capture of this kernel on this workload"
     if tj.get("kernel_sources_sha") != kernel_sources_sha():
         return None, "stale: captured on other kernel sources (%s), not reported" % tj.get("kernel_sources_sha")

@@ -1,9 +1,6 @@
 #!/bin/bash
-# iteration script: parity suite (auto / tile / direct pipelines), short bench, optional ncu of the kernels on cfg3
+# iteration script: parity suite (every test runs under the auto / tile / direct pipelines), short bench, optional ncu of the kernels on cfg3
 mkdir -p gpurun_out
-for pl in 0 1 2; do
-  GELCU_PIPELINE=$pl timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu_p$pl.log 2>&1; echo "pytest pipeline=$pl rc=$?"; tail -3 gpurun_out/pytest_gpu_p$pl.log
-done
-cp gpurun_out/pytest_gpu_p0.log gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
 if [ "$1" != "noprof" ]; then bash scripts/gpu_prof3.sh cfg3 8 direct_raster_kernel d1 8 2; fi
