@@ -98,6 +98,16 @@ __device__ __forceinline__ void st_v4_hint(void* ptr, uint32_t a, uint32_t b, ui
 {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
 }
+template<bool HINT> __device__ __forceinline__ void st_b32(void* ptr, uint32_t v, uint64_t pol)
+{
+    if(HINT) asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(ptr), "r"(v), "l"(pol) : "memory");
+    else *reinterpret_cast<uint32_t*>(ptr) = v;
+}
+template<bool HINT> __device__ __forceinline__ void st_b64(void* ptr, unsigned long long v, uint64_t pol)
+{
+    if(HINT) asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" :: "l"(ptr), "l"(v), "l"(pol) : "memory");
+    else *reinterpret_cast<unsigned long long*>(ptr) = v;
+}
 template<bool HINT>
 __device__ __forceinline__ void key_max(unsigned long long* ptr, unsigned long long key, uint64_t pol)
 {
@@ -492,10 +502,11 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, const float4
 
 /* D5a: reset (main.c:413-417) of everything outside the view's region -- pure stores.
  * grid (ceil(yres / 1024), xres, nviews): a thread owns 4 consecutive rows of one column (regions are 8-aligned) */
-template<bool HASH>
+template<bool HASH, bool HINT>
 __global__ void __launch_bounds__(256)
 direct_fill_kernel(DirectParams p)
 {
+    const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
     const int view = blockIdx.z, x = blockIdx.y;
     const int y4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     int rx0, rx1, ry0, ry1;
@@ -506,8 +517,12 @@ direct_fill_kernel(DirectParams p)
         const size_t base = (size_t) view * p.xres * p.yres + (size_t) x * p.yres;
         if((p.yres & 3) == 0)
         {
-            *reinterpret_cast<uint4*>(p.pixel + base + y4) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<float4*>(p.zbuf + base + y4) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            if(HINT) { st_v4_hint(p.pixel + base + y4, 0u, 0u, 0u, 0u, pol); st_v4_hint(p.zbuf + base + y4, 0xFF7FFFFFu, 0xFF7FFFFFu, 0xFF7FFFFFu, 0xFF7FFFFFu, pol); }
+            else
+            {
+                *reinterpret_cast<uint4*>(p.pixel + base + y4) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<float4*>(p.zbuf + base + y4) = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            }
         }
         for(int k = 0; k < 4; k++)
         {
@@ -585,10 +600,11 @@ direct_fill_persistent_kernel(DirectParams p, int sleep_ns)
  * compact footprint is what keeps the gathers cheap: a warp's 32 pixels then touch few distinct triangles, vertices
  * and -- above all -- texture rows (a 1 x 32 column touched ~30 texture lines per texel load, the L1 data pipe was
  * the kernel's limit), and neighbouring warps reuse the same lines out of L1. */
-template<bool HASH, bool COMPACT>
+template<bool HASH, bool COMPACT, bool HINT>
 __global__ void __launch_bounds__(256, GEL_RESOLVE_MINB)
 direct_resolve_kernel(DirectParams p)
 {
+    const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;          /* frames are written once and not read again by this path */
     constexpr int WROWS = 32 / RESOLVE_WCOLS, WARPS_X = 8 / RESOLVE_WCOLS, WARPS_Y = 8 / WARPS_X, CTA_ROWS = WROWS * WARPS_Y;
     const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = (warp % WARPS_X) * RESOLVE_WCOLS + lane / WROWS, py = (warp / WARPS_X) * WROWS + lane % WROWS;
@@ -618,9 +634,9 @@ direct_resolve_kernel(DirectParams p)
             if(y + CTA_ROWS <= ry1) next_key = vkeys[off + CTA_ROWS];         /* one iteration ahead of its use */
             uint32_t colour; float z;
             direct_shade<COMPACT>(p, xf, vflags, twm1, thm1, key, x, y, colour, z);
-            vkeys[off] = CLEAR_KEY;                                       /* the buffer is all "no winner" again for the next batch */
-            vpixel[off] = colour;
-            vz[off] = z;
+            st_b64<HINT>(vkeys + off, CLEAR_KEY, pol);                    /* the buffer is all "no winner" again for the next batch */
+            st_b32<HINT>(vpixel + off, colour, pol);
+            st_b32<HINT>(vz + off, __float_as_uint(z), pol);
             if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
         }
     }

@@ -50,7 +50,7 @@ struct gelcu_ctx
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr, hi_stream = nullptr, aux_stream = nullptr;   /* side / hi: HBM-bound fill beside the raster kernels (hi = higher priority); aux: small result copies */
     cudaEvent_t side_go = nullptr, side_done = nullptr, stats_go = nullptr, stats_ready[2] = { nullptr, nullptr };
-    int fill_mode = 0, fill_ctas = 1, red_hint = 0, fill_sleep_ns = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
+    int fill_mode = 0, fill_ctas = 1, red_hint = 1, store_hint = 0, fill_sleep_ns = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr; bool trec_compact = false, allow_compact = true;
@@ -228,8 +228,8 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             else
             {
                 const dim3 fgrid((c->yres + 1023) / 1024, c->xres, n);
-                if(want_hash) direct_fill_kernel<true><<<fgrid, 256, 0, fs>>>(dp);
-                else direct_fill_kernel<false><<<fgrid, 256, 0, fs>>>(dp);
+                if(c->store_hint & 1) { if(want_hash) direct_fill_kernel<true, true><<<fgrid, 256, 0, fs>>>(dp); else direct_fill_kernel<false, true><<<fgrid, 256, 0, fs>>>(dp); }
+                else { if(want_hash) direct_fill_kernel<true, false><<<fgrid, 256, 0, fs>>>(dp); else direct_fill_kernel<false, false><<<fgrid, 256, 0, fs>>>(dp); }
             }
             CU(cudaEventRecord(c->side_done, fs));
             c->stats.kernels_launched++;
@@ -252,8 +252,20 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             c->stats.kernels_launched += 2;
         }
         const dim3 sgrid(std::min(RESOLVE_CTAS, (c->xres + 7) / 8), n);   /* one strip of 8 columns per CTA when the grid allows; CTAs past the region's last strip exit at once */
-        if(c->trec_compact) { if(want_hash) direct_resolve_kernel<true, true><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, true><<<sgrid, 256, 0, s>>>(dp); }
-        else { if(want_hash) direct_resolve_kernel<true, false><<<sgrid, 256, 0, s>>>(dp); else direct_resolve_kernel<false, false><<<sgrid, 256, 0, s>>>(dp); }
+        {
+            const int variant = (want_hash ? 4 : 0) | (c->trec_compact ? 2 : 0) | ((c->store_hint & 2) ? 1 : 0);
+            switch(variant)
+            {
+                case 0: direct_resolve_kernel<false, false, false><<<sgrid, 256, 0, s>>>(dp); break;
+                case 1: direct_resolve_kernel<false, false, true><<<sgrid, 256, 0, s>>>(dp); break;
+                case 2: direct_resolve_kernel<false, true, false><<<sgrid, 256, 0, s>>>(dp); break;
+                case 3: direct_resolve_kernel<false, true, true><<<sgrid, 256, 0, s>>>(dp); break;
+                case 4: direct_resolve_kernel<true, false, false><<<sgrid, 256, 0, s>>>(dp); break;
+                case 5: direct_resolve_kernel<true, false, true><<<sgrid, 256, 0, s>>>(dp); break;
+                case 6: direct_resolve_kernel<true, true, false><<<sgrid, 256, 0, s>>>(dp); break;
+                default: direct_resolve_kernel<true, true, true><<<sgrid, 256, 0, s>>>(dp); break;
+            }
+        }
         c->stats.kernels_launched++;
         CU(cudaStreamWaitEvent(s, c->side_done, 0));                    /* the batch ends when its frames are complete: resolve AND fill */
     }
@@ -596,6 +608,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_mode must be 0, 1 or 2"); c->fill_mode = value; }
     else if(!strcmp(name, "fill_ctas_per_sm")) { if(value < 1 || value > 8) return fail(GELCU_E_INVALID, "fill_ctas_per_sm out of [1,8]"); c->fill_ctas = value; }
     else if(!strcmp(name, "red_hint")) c->red_hint = value != 0;
+    else if(!strcmp(name, "store_hint")) { if(value < 0 || value > 3) return fail(GELCU_E_INVALID, "store_hint must be 0..3 (bit 0: fill stores, bit 1: resolve stores evict-first)"); c->store_hint = value; }
     else if(!strcmp(name, "fill_sleep_ns")) { if(value < 0 || value > 1000000) return fail(GELCU_E_INVALID, "fill_sleep_ns out of [0, 1000000]"); c->fill_sleep_ns = value; }
     else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }
     else return fail(GELCU_E_INVALID, "unknown option '%s'", name);
