@@ -135,6 +135,33 @@ transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict_
     }
 }
 
+/* Batch initialisation in ONE launch (it used to be an H2D copy of the initial statistics and up to six memsets, each a
+ * launch of its own -- a third of the device time of a single-view call): per-view statistics, pool cursors, flags, checksums
+ * and, for the tile pipeline, chain heads (-1), lit flags and the two work queues. */
+__global__ void __launch_bounds__(256)
+batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint32_t* __restrict__ flags, unsigned long long* __restrict__ hash,
+                  int* __restrict__ heads, int* __restrict__ tile_lit, int* __restrict__ work, int nviews, int ntiles, int want_hash)
+{
+    const size_t i0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+    if(i0 < (size_t) nviews)
+    {
+        uint32_t* w = vstat + VIEW_STAT_WORDS * i0;
+        w[0] = 0xFFFFFFFFu; w[1] = 0u;                                     /* depth range (min of keys, max of keys) */
+        w[2] = 0x7FFFFFFFu; w[3] = 0x80000000u; w[4] = 0x7FFFFFFFu; w[5] = 0x80000000u;   /* screen bbox (int min / max) */
+        w[6] = 0u; w[7] = 0u;
+        cursors[4 * i0] = 0; cursors[4 * i0 + 1] = 0; cursors[4 * i0 + 2] = 0; cursors[4 * i0 + 3] = 0;
+        flags[i0] = 0u;
+        if(want_hash) { hash[2 * i0] = 0ull; hash[2 * i0 + 1] = 0ull; }
+    }
+    if(heads)
+    {
+        if(i0 < 2) work[i0] = 0;
+        const size_t nlit = (size_t) nviews * ntiles, nheads = nlit * NCHAIN;
+        for(size_t i = i0; i < nheads; i += stride) heads[i] = -1;
+        for(size_t i = i0; i < nlit; i += stride) tile_lit[i] = 0;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* K2: setup + binning                                                                              */
 /* ------------------------------------------------------------------------------------------------ */

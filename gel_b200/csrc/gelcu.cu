@@ -3,7 +3,7 @@
  *
  * Replaces /root/reference main.c:505-522 (reset, per-triangle transform, tdraw) for batches of views.
  * Per batch of B views, all on one stream with no host sync inside:
- *     memset heads/cursors/flags -> K1 transform_kernel -> K2 bin_kernel -> K3 raster_kernel
+ *     batch_init_kernel -> K1 transform_kernel -> K2 bin_kernel -> K3 raster_kernel
  * (K3 also resets the tiles no triangle touched, as background stores between its work items).
  * Meshes of tiny triangles take the DIRECT pipeline instead (gel_direct.cuh):
  *     K1 -> D0 clear keys -> D1 near triangles -> D2 hi-Z -> D3 parked triangles -> D5 resolve/shade.
@@ -68,11 +68,14 @@ struct gelcu_ctx
     uint8_t* d_rgb[2] = { nullptr, nullptr };   /* frame sink: upright 24-bit frames, allocated on first use */
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; uint32_t* h_vstat = nullptr; int hcap = 0;
-    uint32_t* h_vinit = nullptr;   /* pinned initial per-view statistics (VIEW_STAT_WORDS each) x MAX_BATCH */
     std::vector<cudaEvent_t> ev;   /* EV_PER_BATCH per batch */
     cudaEvent_t render_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
     int last_batch_views = 0, last_buf = 0;
     gelcu_stats stats = {};
+    /* small calls (the interactive drop-in: one view per call) replay a captured CUDA graph instead of ~20 API calls */
+    int use_graph = 1; unsigned state_gen = 0; bool keys_dirty_at_entry = false;                              /* state_gen: bumped whenever a buffer, the mesh, the texture or an option changes */
+    cudaGraphExec_t graph_exec = nullptr; unsigned graph_gen = 0; int graph_n = 0, graph_flags = -1; uint64_t graph_kernels = 0, graph_d2h = 0;
+    gelcu_view* h_views = nullptr; unsigned long long* h_hash = nullptr;   /* pinned staging for the graph's fixed-address copies */
     std::vector<std::pair<int, Rect> > pending_rects, done_rects;   /* region output: (view, rectangle) copied, resets pending / done */
 };
 
@@ -97,6 +100,7 @@ void free_work(gelcu_ctx* c)
 #define GEL_RESOLVE_CTAS 1024
 #endif
 constexpr int RESOLVE_CTAS = GEL_RESOLVE_CTAS;  /* most CTAs per view in the direct pipeline's resolve pass (each walks strips of 8 columns) */
+constexpr int GRAPH_MAX_VIEWS = 4;   /* calls of up to this many views (one batch) replay a captured graph */
 constexpr int EV_PER_BATCH = 5;   /* start, after K1, after bin/clear, after the dominant raster kernel, end */
 
 int active_pipeline(const gelcu_ctx* c) { return c->pipeline_opt ? c->pipeline_opt : c->pipeline_auto; }
@@ -147,14 +151,14 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
             CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
             CU(cudaMalloc(&c->d_z[k], sizeof(float) * B * frame));
         }
-        c->batch = B; c->work_pipeline = pipe;
+        c->batch = B; c->work_pipeline = pipe; c->state_gen++;
     }
     if(pipe != 2 && !(c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_entries))
     {
         free_bins(c);
         CU(cudaMalloc(&c->d_entries, sizeof(uint32_t) * std::max<size_t>(1, (size_t) c->batch * cap_e)));
         CU(cudaMalloc(&c->d_descs, sizeof(uint4) * std::max<size_t>(1, (size_t) c->batch * cap_d)));
-        c->cap_e = cap_e; c->cap_d = cap_d;
+        c->cap_e = cap_e; c->cap_d = cap_d; c->state_gen++;
     }
     return GELCU_OK;
 }
@@ -167,27 +171,24 @@ int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 }
 
 /* Enqueues the kernels for `n` views starting at d_views + first into frame buffer `buf`. */
-int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool want_rgb, bool want_stats, cudaEvent_t* ev)
+int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool want_rgb, bool want_stats, cudaEvent_t* ev /* null: no timing events (graph capture) */)
 {
     cudaStream_t s = c->stream;
     const int pipe = c->work_pipeline;
-    CU(cudaMemcpyAsync(c->d_vstat, c->h_vinit, sizeof(uint32_t) * VIEW_STAT_WORDS * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(c->d_cursors, 0, sizeof(int) * 4 * n, s));
-    CU(cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t) * n, s));
-    if(want_hash) CU(cudaMemsetAsync(c->d_hash, 0, sizeof(unsigned long long) * 2 * n, s));
-    if(pipe != 2)
     {
-        CU(cudaMemsetAsync(c->d_heads, 0xFF, sizeof(int) * (size_t) n * c->ntiles * NCHAIN, s));
-        CU(cudaMemsetAsync(c->d_tile_lit, 0, sizeof(int) * (size_t) n * c->ntiles, s));
-        CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(int), s));
+        const size_t cells = pipe != 2 ? (size_t) n * c->ntiles * NCHAIN : (size_t) n;
+        const int grid = (int) std::min<size_t>((size_t) c->num_sms * 8, std::max<size_t>(1, (cells / 4 + 255) / 256));
+        batch_init_kernel<<<grid, 256, 0, s>>>(c->d_vstat, c->d_cursors, c->d_flags, c->d_hash, pipe != 2 ? c->d_heads : nullptr, c->d_tile_lit, c->d_work,
+                                               n, c->ntiles, want_hash ? 1 : 0);
+        c->stats.kernels_launched++;
     }
-    CU(cudaEventRecord(ev[0], s));
+    if(ev) CU(cudaEventRecord(ev[0], s));
     if(c->nuniq > 0)
     {
         transform_kernel<<<dim3((c->nuniq + 256 * XF_PER_THREAD - 1) / (256 * XF_PER_THREAD), n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->d_vstat, c->nuniq, c->xres, c->yres);
         c->stats.kernels_launched++;
     }
-    CU(cudaEventRecord(ev[1], s));
+    if(ev) CU(cudaEventRecord(ev[1], s));
     if(want_stats)
     {
         /* region output: the per-view vertex statistics (complete after K1) go to the host on their own stream while
@@ -196,6 +197,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         CU(cudaStreamWaitEvent(c->aux_stream, c->stats_go, 0));
         CU(cudaMemcpyAsync(c->h_vstat + (size_t) VIEW_STAT_WORDS * first, c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * n, cudaMemcpyDeviceToHost, c->aux_stream));
         CU(cudaEventRecord(c->stats_ready[buf], c->aux_stream));
+        if(!ev) CU(cudaStreamWaitEvent(s, c->stats_ready[buf], 0));       /* under capture every forked stream has to join again */
         c->stats.d2h_bytes += sizeof(uint32_t) * VIEW_STAT_WORDS * (size_t) n;
     }
     if(pipe == 2)
@@ -206,7 +208,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         const dim3 rgrid((c->ntri + tris_per_cta - 1) / tris_per_cta, n);
         direct_clear_kernel<<<dim3(64, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
-        CU(cudaEventRecord(ev[2], s));
+        if(ev) CU(cudaEventRecord(ev[2], s));
         CU(cudaEventRecord(c->side_go, s));                              /* the region is known from here on */
         /* Reset (main.c:413-417) of everything outside the view's region: pure stores, beside the raster kernels.
          *   fill_mode 0: a plain grid on the side stream, submitted AFTER the near pass -- it fills in as the near pass
@@ -242,7 +244,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             else direct_raster_kernel<0, false><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched++;
         }
-        CU(cudaEventRecord(ev[3], s));
+        if(ev) CU(cudaEventRecord(ev[3], s));
         if(!early_fill) { const int rc = launch_fill(); if(rc) return rc; }
         if(c->ntri > 0)
         {
@@ -278,7 +280,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
             c->stats.kernels_launched++;
         }
-        CU(cudaEventRecord(ev[2], s));
+        if(ev) CU(cudaEventRecord(ev[2], s));
         RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_vstat, c->d_far,
                             c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
                             c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
@@ -286,9 +288,9 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
         else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
         c->stats.kernels_launched++;
-        CU(cudaEventRecord(ev[3], s));
+        if(ev) CU(cudaEventRecord(ev[3], s));
     }
-    CU(cudaEventRecord(ev[4], s));
+    if(ev) CU(cudaEventRecord(ev[4], s));
     if(want_rgb)
     {
         /* frame sink: un-rotated 24-bit copy for the device -> host transfer; after the path's last
@@ -319,7 +321,7 @@ int ensure_host(gelcu_ctx* c, int n)
     CU(cudaMallocHost(&c->h_cursors, sizeof(int) * 4 * n));
     CU(cudaMallocHost(&c->h_flags, sizeof(uint32_t) * n));
     CU(cudaMallocHost(&c->h_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * n));
-    c->hcap = n;
+    c->hcap = n; c->state_gen++;
     return GELCU_OK;
 }
 
@@ -329,7 +331,7 @@ int choose_pipeline(int ntri, double mean_tri_px) { return (ntri >= 65536 && mea
 
 void drop_mesh(gelcu_ctx* c)
 {
-    c->have_mesh = false; c->ntri = 0; c->nuniq = 0;
+    c->have_mesh = false; c->ntri = 0; c->nuniq = 0; c->state_gen++;
     free_work(c);
     dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
 }
@@ -397,14 +399,6 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
         if(s2 == cudaSuccess) s2 = cudaEventCreateWithFlags(&c->stats_ready[k], cudaEventDisableTiming);
     }
     if(s1 != cudaSuccess || s2 != cudaSuccess) { delete c; return fail(GELCU_E_CUDA, "stream/event creation failed"); }
-    if(cudaMallocHost(&c->h_vinit, sizeof(uint32_t) * VIEW_STAT_WORDS * MAX_BATCH) != cudaSuccess) { delete c; return fail(GELCU_E_NOMEM, "pinned allocation failed"); }
-    for(int v = 0; v < MAX_BATCH; v++)
-    {
-        uint32_t* w = c->h_vinit + VIEW_STAT_WORDS * v;
-        w[0] = 0xFFFFFFFFu; w[1] = 0u;                                     /* depth range        */
-        w[2] = 0x7FFFFFFFu; w[3] = 0x80000000u; w[4] = 0x7FFFFFFFu; w[5] = 0x80000000u;   /* screen bbox (int min/max) */
-        w[6] = 0u; w[7] = 0u;                                              /* parked triangles   */
-    }
     *out = c;
     return GELCU_OK;
 }
@@ -594,14 +588,16 @@ int gelcu_set_texture(gelcu_ctx* c, const uint32_t* xrgb, int w, int h)
     dfree(c->d_tex);
     CU(cudaMalloc(&c->d_tex, sizeof(uint32_t) * (size_t) w * h));
     CU(cudaMemcpy(c->d_tex, xrgb, sizeof(uint32_t) * (size_t) w * h, cudaMemcpyHostToDevice));
-    c->tw = w; c->th = h;
+    c->tw = w; c->th = h; c->state_gen++;
     return GELCU_OK;
 }
 
 int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
 {
     if(!c || !name) return fail(GELCU_E_INVALID, "null argument");
-    if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
+    c->state_gen++;
+    if(!strcmp(name, "graph_small_calls")) c->use_graph = value != 0;
+    else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
@@ -683,7 +679,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
     {
         dfree(c->d_views);
         CU(cudaMalloc(&c->d_views, sizeof(gelcu_view) * nviews));
-        c->views_cap = nviews;
+        c->views_cap = nviews; c->state_gen++;
     }
     rc = ensure_host(c, nviews); if(rc) return rc;
     const int nchunks = (c->ntri + BIN_CHUNK - 1) / BIN_CHUNK;
@@ -697,7 +693,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         const int B = std::min(nviews, std::max(c->batch, default_batch(c, cap_e, cap_d)));
         rc = ensure_work(c, B, cap_e, cap_d); if(rc) return rc;
         if(rgb_out && !c->d_rgb[0])
-            for(int k = 0; k < 2; k++) CU(cudaMalloc(&c->d_rgb[k], 3 * frame * (size_t) c->batch));
+        { for(int k = 0; k < 2; k++) CU(cudaMalloc(&c->d_rgb[k], 3 * frame * (size_t) c->batch)); c->state_gen++; }
         /* frames that go back to the host: a call is cut into at least four batches so that the copy of one batch
          * runs under the rendering of the next (the copy is the longer of the two by an order of magnitude) */
         int bsz = std::min(c->batch, nviews);
@@ -705,8 +701,8 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         const int nb = (nviews + bsz - 1) / bsz;
         rc = ensure_events(c, nb); if(rc) return rc;
         c->stats.kernels_launched = 0; c->stats.h2d_bytes = 0; c->stats.d2h_bytes = 0; c->stats.batches = nb; c->stats.views = nviews;
-        CU(cudaMemcpyAsync(c->d_views, views, sizeof(gelcu_view) * nviews, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += sizeof(gelcu_view) * (size_t) nviews;
+        c->keys_dirty_at_entry = c->d_keys && c->keys_dirty;
         if(c->d_keys && c->keys_dirty)
         {
             /* the resolve pass leaves the key buffer all "no winner"; only a fresh allocation or a call that failed
@@ -717,6 +713,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         }
         c->keys_dirty = true;
 
+        bool graphed_call = false;
         auto issue_copies = [&](int b) -> int {
             const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
             CU(cudaStreamWaitEvent(c->copy_stream, c->render_done[buf], 0));
@@ -724,7 +721,8 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
             {
                 /* only each view's region crosses PCIe (a strided copy per frame); the strips of the caller's frame that
                  * the previous occupant lit and this view does not are reset here, on the host, while the copies run */
-                CU(cudaEventSynchronize(c->stats_ready[buf]));
+                /* (a graphed call has no usable event inside the graph: it waits for the whole small render) */
+                CU(cudaEventSynchronize(graphed_call ? c->render_done[buf] : c->stats_ready[buf]));
                 for(int v = 0; v < n; v++)
                 {
                     Rect now;
@@ -771,9 +769,51 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         };
         c->pending_rects.clear(); c->done_rects.clear();
 
+        const bool graphed = c->use_graph && nb == 1 && nviews <= GRAPH_MAX_VIEWS && !want_region && !(c->d_keys && c->keys_dirty_at_entry);   /* region calls overlap their copies with the render instead */
+        graphed_call = graphed;
+        if(graphed)
+        {
+            /* Small call: everything up to the frames' own copies is ONE graph launch.  The graph is captured from the same
+             * enqueue code (kernels, the cross-stream fill, the small result copies) the first time a call of this shape
+             * arrives and replayed until a buffer, the mesh, the texture or an option changes (state_gen).  Its copies use
+             * fixed pinned staging: the views go through h_views, the checksums through h_hash. */
+            const int flags_key = (hash_out ? 1 : 0) | (rgb_out ? 2 : 0) | (want_region ? 4 : 0);
+            if(!c->h_views) { CU(cudaMallocHost(&c->h_views, sizeof(gelcu_view) * GRAPH_MAX_VIEWS)); CU(cudaMallocHost(&c->h_hash, 16 * GRAPH_MAX_VIEWS)); }
+            if(!c->graph_exec || c->graph_gen != c->state_gen || c->graph_n != nviews || c->graph_flags != flags_key)
+            {
+                if(c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+                const uint64_t k0 = c->stats.kernels_launched, b0 = c->stats.d2h_bytes;
+                cudaGraph_t graph = nullptr;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int crc = GELCU_OK;
+                cudaError_t ce = cudaMemcpyAsync(c->d_views, c->h_views, sizeof(gelcu_view) * nviews, cudaMemcpyHostToDevice, c->stream);
+                if(ce == cudaSuccess) crc = enqueue_batch(c, 0, nviews, 0, hash_out != nullptr, rgb_out != nullptr, want_region, nullptr);
+                if(ce == cudaSuccess && crc == GELCU_OK) ce = cudaMemcpyAsync(c->h_cursors, c->d_cursors, sizeof(int) * 4 * nviews, cudaMemcpyDeviceToHost, c->stream);
+                if(ce == cudaSuccess && crc == GELCU_OK) ce = cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(uint32_t) * nviews, cudaMemcpyDeviceToHost, c->stream);
+                if(ce == cudaSuccess && crc == GELCU_OK && hash_out) { ce = cudaMemcpyAsync(c->h_hash, c->d_hash, 16 * (size_t) nviews, cudaMemcpyDeviceToHost, c->stream); c->stats.d2h_bytes += 16 * (size_t) nviews; }
+                const cudaError_t ee = cudaStreamEndCapture(c->stream, &graph);
+                if(crc != GELCU_OK) { if(graph) cudaGraphDestroy(graph); return crc; }
+                if(ce != cudaSuccess || ee != cudaSuccess) { if(graph) cudaGraphDestroy(graph); return fail(GELCU_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee)); }
+                const cudaError_t ie = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if(ie != cudaSuccess) { c->graph_exec = nullptr; return fail(GELCU_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+                c->graph_gen = c->state_gen; c->graph_n = nviews; c->graph_flags = flags_key;
+                c->graph_kernels = c->stats.kernels_launched - k0; c->graph_d2h = c->stats.d2h_bytes - b0;
+                c->stats.kernels_launched = k0; c->stats.d2h_bytes = b0;
+            }
+            memcpy(c->h_views, views, sizeof(gelcu_view) * nviews);
+            CU(cudaEventRecord(c->ev[0], c->stream));
+            CU(cudaGraphLaunch(c->graph_exec, c->stream));
+            CU(cudaEventRecord(c->ev[4], c->stream));
+            CU(cudaEventRecord(c->render_done[0], c->stream));
+            c->stats.kernels_launched += c->graph_kernels; c->stats.d2h_bytes += c->graph_d2h;
+            c->last_batch_views = nviews; c->last_buf = 0;
+        }
+        else
         for(int b = 0; b < nb; b++)
         {
             const int buf = b & 1, first = b * bsz, n = std::min(bsz, nviews - first);
+            if(b == 0) CU(cudaMemcpyAsync(c->d_views, views, sizeof(gelcu_view) * nviews, cudaMemcpyHostToDevice, c->stream));
             if(b >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[buf], 0));
             if(want_region && b >= 1) CU(cudaStreamWaitEvent(c->stream, c->stats_ready[(b - 1) & 1], 0));   /* d_vstat is reused */
             rc = enqueue_batch(c, first, n, buf, hash_out != nullptr, rgb_out != nullptr, want_region, &c->ev[EV_PER_BATCH * b]); if(rc) return rc;
@@ -792,6 +832,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         CU(cudaStreamSynchronize(c->hi_stream));
         CU(cudaStreamSynchronize(c->aux_stream));
         c->keys_dirty = false;
+        if(graphed && hash_out) memcpy(hash_out, c->h_hash, 16 * (size_t) nviews);
 
         uint32_t flags = 0; int need_e = 0, need_d = 0; uint64_t entries = 0;
         for(int v = 0; v < nviews; v++)
@@ -824,7 +865,7 @@ int render_impl(gelcu_ctx* c, const gelcu_view* views, int nviews,
         {
             cudaEvent_t* e = &c->ev[EV_PER_BATCH * b];
             CU(cudaEventElapsedTime(&t, e[0], e[4])); ms += t;
-            if(c->stage_timing)
+            if(c->stage_timing && !graphed)
             {
                 CU(cudaEventElapsedTime(&t, e[0], e[1])); c->stats.ms_transform += t;
                 CU(cudaEventElapsedTime(&t, e[1], e[2])); c->stats.ms_bin += t;
@@ -952,10 +993,12 @@ void gelcu_destroy(gelcu_ctx* c)
     dfree(c->d_tex); dfree(c->d_views);
     if(c->h_cursors) cudaFreeHost(c->h_cursors);
     if(c->h_flags) cudaFreeHost(c->h_flags);
-    if(c->h_vinit) cudaFreeHost(c->h_vinit);
     if(c->h_vstat) cudaFreeHost(c->h_vstat);
     for(cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for(int k = 0; k < 2; k++) { if(c->render_done[k]) cudaEventDestroy(c->render_done[k]); if(c->copy_done[k]) cudaEventDestroy(c->copy_done[k]); if(c->stats_ready[k]) cudaEventDestroy(c->stats_ready[k]); }
+    if(c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if(c->h_views) cudaFreeHost(c->h_views);
+    if(c->h_hash) cudaFreeHost(c->h_hash);
     if(c->hi_stream) cudaStreamDestroy(c->hi_stream);
     if(c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if(c->stats_go) cudaEventDestroy(c->stats_go);

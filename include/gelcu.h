@@ -143,7 +143,11 @@ int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out
  *   "stage_timing"  1 = record per-stage CUDA events into gelcu_stats (default 1)
  *   "pipeline"      0 = chosen from the mesh (default), 1 = tile pipeline, 2 = direct pipeline
  *   "compact_records"  1 (default) = meshes with fewer than 2^21 distinct vertices get 32-byte per-triangle shading
- *                   records (three 21-bit indices), 0 = always the 64-byte form; read by the next gelcu_set_mesh */
+ *                   records (three 21-bit indices), 0 = always the 64-byte form; read by the next gelcu_set_mesh
+ *   "graph_small_calls"  1 (default) = calls of up to 4 views replay a captured CUDA graph (one launch instead of ~20 API calls:
+ *                   the interactive one-view-per-frame use); stage timings are not recorded for such calls
+ *   "fill_mode", "fill_ctas_per_sm", "fill_sleep_ns", "red_hint", "store_hint"   direct pipeline experiments with the background
+ *                   reset and L2 cache-policy hints (defaults: plain trailing fill, evict-last hint on the key REDs) */
 int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
 int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
 
