@@ -595,6 +595,76 @@ direct_fill_persistent_kernel(DirectParams p, int sleep_ns)
     flush_hash();
 }
 
+/* D5a, bulk form (sm_90+ / sm_100a): the same reset issued as TMA bulk stores -- `cp.async.bulk.global.shared::cta` (SASS
+ * UBLKCP) copies of a constant pattern held in shared memory (zeros for the pixels, 0xFF7FFFFF = -FLT_MAX for z).  One elected
+ * thread per CTA issues a copy per 8 KB of frame, so the 3.3 GB per cfg-3 step cost a few hundred thousand instructions instead of
+ * the 245 M warp-instructions of the store loop: the fill stops competing with the instruction-bound near pass for issue slots and
+ * LSU queues and can run underneath it.  Needs yres % 4 == 0 (16-byte granules); the caller falls back to the store loop otherwise,
+ * and whenever checksums are requested (those are computed per reset pixel).
+ *   per view: the frame as a flat word array; everything left of the region's first column and right of its last one is two
+ *   contiguous ranges, cut into BULK_BYTES pieces; inside the region's columns the rows below / above the region are one strip each. */
+constexpr int BULK_BYTES = 8192;
+__device__ __forceinline__ void bulk_store(void* gptr, uint32_t smem_addr, uint32_t bytes, uint64_t pol, bool hint)
+{
+    if(hint) asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" :: "l"(gptr), "r"(smem_addr), "r"(bytes), "l"(pol) : "memory");
+    else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gptr), "r"(smem_addr), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(32)
+direct_fill_bulk_kernel(DirectParams p, int hint)
+{
+    __shared__ __align__(128) uint32_t pat_pixel[BULK_BYTES / 4];
+    __shared__ __align__(128) uint32_t pat_z[BULK_BYTES / 4];
+    for(int i = threadIdx.x; i < BULK_BYTES / 4; i += 32) { pat_pixel[i] = 0u; pat_z[i] = 0xFF7FFFFFu; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        /* the pattern is read by the async proxy */
+    __syncwarp();
+    if(threadIdx.x != 0) return;
+    const uint64_t pol = hint ? l2_policy_evict_first() : 0ull;
+    const uint32_t sp = (uint32_t) __cvta_generic_to_shared(pat_pixel), sz = (uint32_t) __cvta_generic_to_shared(pat_z);
+    const size_t frame = (size_t) p.xres * p.yres, frame_bytes = frame * 4;
+    const int pieces = (int) ((frame_bytes + BULK_BYTES - 1) / BULK_BYTES);
+    const int per_view = pieces + p.xres;                               /* flat pieces, then one item per column (strips) */
+    const long long nitems = (long long) p.nviews * per_view;
+    for(long long item = blockIdx.x; item < nitems; item += gridDim.x)
+    {
+        const int view = (int) (item / per_view), k = (int) (item - (long long) view * per_view);
+        int rx0, rx1, ry0, ry1;
+        const bool any = load_region(p, view, rx0, rx1, ry0, ry1);
+        char* pix = reinterpret_cast<char*>(p.pixel + (size_t) view * frame);
+        char* zb = reinterpret_cast<char*>(p.zbuf + (size_t) view * frame);
+        if(k < pieces)
+        {
+            /* flat piece [b0, b1) minus the region's column range [r0, r1) (bytes): at most one part on either side */
+            const size_t b0 = (size_t) k * BULK_BYTES, b1 = min(b0 + (size_t) BULK_BYTES, frame_bytes);
+            const size_t r0 = any ? (size_t) rx0 * p.yres * 4 : frame_bytes, r1 = any ? (size_t) (rx1 + 1) * p.yres * 4 : frame_bytes;
+            const size_t a1 = min(b1, r0);                               /* part left of the region */
+            if(a1 > b0) { bulk_store(pix + b0, sp, (uint32_t) (a1 - b0), pol, hint); bulk_store(zb + b0, sz, (uint32_t) (a1 - b0), pol, hint); }
+            const size_t c0 = max(b0, r1);                               /* part right of it */
+            if(b1 > c0) { bulk_store(pix + c0, sp, (uint32_t) (b1 - c0), pol, hint); bulk_store(zb + c0, sz, (uint32_t) (b1 - c0), pol, hint); }
+        }
+        else if(any)
+        {
+            const int x = k - pieces;
+            if(x < rx0 || x > rx1) continue;
+            const size_t col = (size_t) x * p.yres * 4;
+            for(size_t o = 0; o < (size_t) ry0 * 4; o += BULK_BYTES)
+            {
+                const uint32_t n = (uint32_t) min((size_t) BULK_BYTES, (size_t) ry0 * 4 - o);
+                bulk_store(pix + col + o, sp, n, pol, hint); bulk_store(zb + col + o, sz, n, pol, hint);
+            }
+            for(size_t o = (size_t) (ry1 + 1) * 4; o < (size_t) p.yres * 4; o += BULK_BYTES)
+            {
+                const uint32_t n = (uint32_t) min((size_t) BULK_BYTES, (size_t) p.yres * 4 - o);
+                bulk_store(pix + col + o, sp, n, pol, hint); bulk_store(zb + col + o, sz, n, pol, hint);
+            }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");    /* bound the copies in flight per CTA */
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             /* every store has landed before the kernel ends */
+}
+
 /* D5b: every pixel inside the region: winner shaded once or reset.  grid (G, nviews): a CTA takes strips of 8
  * adjacent columns, 32 rows at a time; a warp covers RESOLVE_WCOLS columns x (32 / RESOLVE_WCOLS) rows of them.  The
  * compact footprint is what keeps the gathers cheap: a warp's 32 pixels then touch few distinct triangles, vertices

@@ -50,7 +50,7 @@ struct gelcu_ctx
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr, hi_stream = nullptr, aux_stream = nullptr;   /* side / hi: HBM-bound fill beside the raster kernels (hi = higher priority); aux: small result copies */
     cudaEvent_t side_go = nullptr, side_done = nullptr, stats_go = nullptr, stats_ready[2] = { nullptr, nullptr };
-    int fill_mode = 0, fill_ctas = 1, red_hint = 1, store_hint = 0, fill_sleep_ns = 0;   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
+    int fill_mode = 0, fill_ctas = 1, red_hint = 1, store_hint = 0, fill_sleep_ns = 0, fill_after = 0;   /* fill_after: trailing fill starts 0 = as the near pass drains, 1 = when it has ended, 2 = after the parked pass */   /* direct pipeline, background reset: 0 = plain grid after the near pass, 1 = persistent grid under it with evict-first stores, 2 = the same without the hint */
     /* mesh: distinct (position, normal) corners + per-triangle indices and texture coordinates */
     int ntri = 0, nuniq = 0; bool have_mesh = false, keys_dirty = true;
     float4 *d_vpos = nullptr, *d_vnrm = nullptr; uint32_t *d_i0 = nullptr, *d_i1 = nullptr, *d_i2 = nullptr; float2* d_uv = nullptr; uint4* d_trec = nullptr; bool trec_compact = false, allow_compact = true;
@@ -217,14 +217,23 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
          *                evict-first stores: the 51 MB per cfg-3 frame stream out underneath the issue-bound near pass
          *                (which uses a fifth of the DRAM bandwidth) without evicting the L2-resident key buffer;
          *   fill_mode 2: mode 1 without the cache hint (the control of that experiment). */
-        const bool early_fill = c->fill_mode != 0;
+        /*   fill_mode 3 / 4: TMA bulk stores (direct_fill_bulk_kernel) from a persistent grid, submitted before (3) or after (4)
+         *                the near pass; 5 = 3 with the evict-first hint.  Frames whose height is not a multiple of 4, and calls
+         *                that want checksums, use the store loops. */
+        const bool bulk_ok = (c->yres & 3) == 0 && !want_hash;
+        const int fmode = (c->fill_mode >= 3 && !bulk_ok) ? 0 : c->fill_mode;
+        const bool early_fill = fmode == 1 || fmode == 2 || fmode == 3 || fmode == 5;
         cudaStream_t fs = early_fill ? c->hi_stream : c->side_stream;
         auto launch_fill = [&]() -> int {
             CU(cudaStreamWaitEvent(fs, c->side_go, 0));
-            if(early_fill)
+            if(fmode >= 3)
+            {
+                direct_fill_bulk_kernel<<<c->num_sms * std::max(1, std::min(c->fill_ctas, 8)), 32, 0, fs>>>(dp, fmode == 5 ? 1 : 0);
+            }
+            else if(early_fill)
             {
                 const int grid = c->num_sms * std::max(1, std::min(c->fill_ctas, 8));
-                if(c->fill_mode == 1) { if(want_hash) direct_fill_persistent_kernel<true, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); else direct_fill_persistent_kernel<false, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); }
+                if(fmode == 1) { if(want_hash) direct_fill_persistent_kernel<true, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); else direct_fill_persistent_kernel<false, true><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); }
                 else { if(want_hash) direct_fill_persistent_kernel<true, false><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); else direct_fill_persistent_kernel<false, false><<<grid, 256, 0, fs>>>(dp, c->fill_sleep_ns); }
             }
             else
@@ -245,7 +254,8 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             c->stats.kernels_launched++;
         }
         if(ev) CU(cudaEventRecord(ev[3], s));
-        if(!early_fill) { const int rc = launch_fill(); if(rc) return rc; }
+        if(!early_fill && c->fill_after == 1) CU(cudaEventRecord(c->side_go, s));      /* the fill waits for the END of the near pass */
+        if(!early_fill && c->fill_after != 2) { const int rc = launch_fill(); if(rc) return rc; }
         if(c->ntri > 0)
         {
             direct_hiz_kernel<<<dim3(32, n), 256, 0, s>>>(dp);
@@ -253,6 +263,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
             else direct_raster_kernel<1, false><<<rgrid, DIRECT_THREADS, 0, s>>>(dp);
             c->stats.kernels_launched += 2;
         }
+        if(!early_fill && c->fill_after == 2) { CU(cudaEventRecord(c->side_go, s)); const int rc = launch_fill(); if(rc) return rc; }
         const dim3 sgrid(std::min(RESOLVE_CTAS, (c->xres + 7) / 8), n);   /* one strip of 8 columns per CTA when the grid allows; CTAs past the region's last strip exit at once */
         {
             const int variant = (want_hash ? 4 : 0) | (c->trec_compact ? 2 : 0) | ((c->store_hint & 2) ? 1 : 0);
@@ -601,9 +612,10 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
-    else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_mode must be 0, 1 or 2"); c->fill_mode = value; }
+    else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 5) return fail(GELCU_E_INVALID, "fill_mode must be 0..5"); c->fill_mode = value; }
     else if(!strcmp(name, "fill_ctas_per_sm")) { if(value < 1 || value > 8) return fail(GELCU_E_INVALID, "fill_ctas_per_sm out of [1,8]"); c->fill_ctas = value; }
     else if(!strcmp(name, "red_hint")) c->red_hint = value != 0;
+    else if(!strcmp(name, "fill_after")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_after must be 0, 1 or 2"); c->fill_after = value; }
     else if(!strcmp(name, "store_hint")) { if(value < 0 || value > 3) return fail(GELCU_E_INVALID, "store_hint must be 0..3 (bit 0: fill stores, bit 1: resolve stores evict-first)"); c->store_hint = value; }
     else if(!strcmp(name, "fill_sleep_ns")) { if(value < 0 || value > 1000000) return fail(GELCU_E_INVALID, "fill_sleep_ns out of [0, 1000000]"); c->fill_sleep_ns = value; }
     else if(!strcmp(name, "pipeline")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "pipeline must be 0 (auto), 1 (tile) or 2 (direct)"); c->pipeline_opt = value; }

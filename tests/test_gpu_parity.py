@@ -550,6 +550,31 @@ def test_non_finite_vertices_match_the_oracle():
         assert not np.isnan(out["z"]).any()
 
 
+@pytest.mark.parametrize("opts", [{"fill_mode": 1, "fill_sleep_ns": 300}, {"fill_mode": 2, "fill_ctas_per_sm": 2}, {"fill_mode": 3}, {"fill_mode": 4, "fill_ctas_per_sm": 4},
+                                  {"fill_mode": 5, "fill_ctas_per_sm": 2}, {"fill_after": 1, "store_hint": 3}, {"fill_after": 2, "red_hint": 0}])
+def test_direct_pipeline_fill_variants(opts):
+    """The background reset of the direct pipeline in its measured variants: persistent grids with L2 cache-policy
+    hints and pacing, TMA bulk stores (cp.async.bulk, shared -> global) before / after the near pass, later start points, store
+    hints.  Every one must leave exactly the reference's frames -- at a height that allows the 16-byte bulk granules and at one
+    that does not (falls back to the store loop), with and without checksums."""
+    if PIPELINE == 1:
+        pytest.skip("direct pipeline only")
+    rng = np.random.default_rng(606)
+    tv, tn, tt = random_soup(rng, 2500, size=(0.004, 0.05), xr=(-0.15, 0.45), yr=(0.2, 0.8), zspread=0.4)
+    tex = small_tex(rng, 32, 32)
+    bases = gel_b200.view_bases([(0, 0), (0.6, 0.1), (-1.0, 0.0), (2.0, -0.1), (3.0, 0.2)])
+    for (W, H) in ((640, 480), (333, 250)):
+        ref = oracle.render_views(tv, tn, tt, tex, W, H, bases, nthreads=NTHREADS, z=True, hashes=True)
+        with gel_b200.Renderer(W, H) as r:
+            r.set_mesh(tv, tn, tt); r.set_texture(tex); r.set_option("pipeline", 2); r.set_option("batch_views", 2)
+            for k, v in opts.items():
+                r.set_option(k, v)
+            for hashes in (False, True, False):
+                out = r.render(bases, z=True, hashes=hashes)
+                assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])), (W, H, opts, hashes)
+                assert not hashes or np.array_equal(out["hash"], ref["hash"])
+
+
 def test_call_order_and_argument_errors():
     r = gel_b200.Renderer(64, 64)
     with pytest.raises(gel_b200.GelcuError) as e:
