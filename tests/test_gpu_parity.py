@@ -532,6 +532,53 @@ def test_contexts_sharded_like_ranks_match_one_context(cfg1):
     assert np.array_equal(whole[::16], ref["hash"])
 
 
+def test_small_calls_replay_a_graph_and_stay_exact(cfg1):
+    """The interactive pattern: one view per call, many calls (the library replays a captured CUDA graph for calls of up to 4
+    views).  Shapes alternate (1, 3, 1, 2 views, with / without checksums, rgb8, a pageable destination), options and the mesh
+    change in between -- each change re-captures; several contexts do this at once from their own host threads."""
+    import threading
+    tv, tn, tt, tex = cfg1
+    angles = [(0.1 * k, 0.02 * (k % 5)) for k in range(24)]
+    bases = gel_b200.view_bases(angles)
+    W, H = 320, 240
+    ref = oracle.render_views(tv, tn, tt, tex, W, H, bases, nthreads=NTHREADS, z=True, hashes=True)
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            with make_renderer(W, H, tv, tn, tt, tex) as r:
+                k = 0
+                for step in range(40):
+                    n = int(rng.choice([1, 1, 1, 3, 2]))
+                    sel = (np.arange(n) + k) % len(bases); k += n
+                    mode = int(rng.integers(0, 4))
+                    if mode == 0:
+                        out = r.render(bases[sel], z=True, hashes=True)
+                        ok = np.array_equal(out["pixel"], ref["pixel"][sel]) and np.array_equal(bits(out["z"]), bits(ref["z"][sel])) and np.array_equal(out["hash"], ref["hash"][sel])
+                    elif mode == 1:
+                        out = r.render(bases[sel])
+                        ok = np.array_equal(out["pixel"], ref["pixel"][sel])
+                    elif mode == 2:
+                        out = r.render_rgb8(bases[sel])
+                        ok = all(np.array_equal(out["rgb"][j], upright_rgb(ref["pixel"][sel[j]], W, H)) for j in range(n))
+                    else:
+                        r.render(bases[sel], pixels=False)
+                        px, zb = r.read_frame(n - 1)
+                        ok = np.array_equal(px, ref["pixel"][sel[-1]]) and np.array_equal(bits(zb), bits(ref["z"][sel[-1]]))
+                    assert ok, (seed, step, n, mode)
+                    if step == 15:
+                        r.set_option("graph_small_calls", 0)
+                    if step == 25:
+                        r.set_option("graph_small_calls", 1); r.set_mesh(tv, tn, tt)
+        except Exception as e:                                            # noqa: BLE001 -- surfaced below
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(s,)) for s in range(3)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors
+
+
 def test_non_finite_vertices_match_the_oracle():
     """NaN / inf / huge coordinates in a few triangles: a NaN depth never passes `z > zbuff` (main.c:356) and den = NaN never
     draws; the rest of the scene is untouched.  Compared where x86's and CUDA's float->int conversions agree (no NaN in x / y)."""
