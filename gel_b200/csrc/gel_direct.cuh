@@ -50,7 +50,8 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 constexpr int RESOLVE_WCOLS = GEL_RESOLVE_WCOLS;
 constexpr int TREC_QUADS = 4;                    /* wide static record per triangle for the resolve pass: 64 bytes */
 constexpr int TREC_COMPACT_BITS = 21;            /* meshes with < 2^21 distinct vertices: 32-byte record, three 21-bit indices */
-constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through */
+constexpr int DIRECT_TRIS_PER_WARP = GEL_DIRECT_TPW;          /* consecutive triangles a warp streams through (large batches) */
+constexpr int DIRECT_TRIS_PER_WARP_MIN = 128;                  /* ... down to this many when a batch would otherwise leave SMs without warps */
 constexpr int REGION_WORDS = 8;                    /* per view: x0, x1, y0, y1 (block aligned, -1.. when empty), zthr bits */
 constexpr int DIRECT_UNIT_WINDOW = 256;
 constexpr int DIRECT_CAND = 256;                 /* ring of hi-Z survivors waiting for a full batch (phase 1) */
@@ -69,12 +70,13 @@ struct DirectParams
     unsigned long long* keys;      /* [view][xres*yres]  index y + x*yres                                   */
     uint32_t* hiz;                 /* [view][hbx*hby]    min depth key per 8x8 block, index bx*hby + by     */
     uint4* far;                    /* [view][ntri]       parked: tri, x0 | x1 << 16, y0 | y1 << 16, bound; warp w of D1 owns
-                                    *                     records [w*DIRECT_TRIS_PER_WARP, ...) and writes their count to far_count */
+                                    *                     records [w*tpw, ...) and writes their count to far_count */
     int* far_count;                /* [view][warps]                                                         */
     int* region;                   /* [view][REGION_WORDS]  written by D0                                   */
     uint32_t* vstat;               /* [view][VSTAT]                                                         */
     uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags;
     int ntri, nuniq, xres, yres, hbx, hby, nviews;
+    int tpw;                       /* triangles per warp of D1 / D3 for this batch (power of two) */
 };
 
 struct DirectScratch               /* per warp */
@@ -213,10 +215,10 @@ direct_raster_kernel(DirectParams p)
     const uint32_t* hiz = p.hiz + (size_t) view * p.hbx * p.hby;
     const float zthr = PHASE == 0 ? __int_as_float(__ldg(p.region + (size_t) view * REGION_WORDS + 4)) : 0.0f;
     const int gwarp = blockIdx.x * DIRECT_WARPS + warp, nwarps = gridDim.x * DIRECT_WARPS;
-    const int first = gwarp * DIRECT_TRIS_PER_WARP;
+    const int first = gwarp * p.tpw;
     if(first >= p.ntri) return;
     int* my_far_count = p.far_count + (size_t) view * nwarps + gwarp;
-    const int last = PHASE == 0 ? min(first + DIRECT_TRIS_PER_WARP, p.ntri) : first + *my_far_count;
+    const int last = PHASE == 0 ? min(first + p.tpw, p.ntri) : first + *my_far_count;
     int qn = 0, parked = 0;
     bool clipped = false;
 

@@ -135,7 +135,7 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
             c->keys_dirty = true;                                   /* filled with "no winner" before the first batch */
             CU(cudaMalloc(&c->d_hiz, sizeof(uint32_t) * (size_t) B * c->hbx * c->hby));
             CU(cudaMalloc(&c->d_parked, sizeof(uint4) * std::max<size_t>(1, (size_t) B * c->ntri)));
-            CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP + DIRECT_WARPS + 1)));
+            CU(cudaMalloc(&c->d_far_count, sizeof(int) * (size_t) B * (c->ntri / DIRECT_TRIS_PER_WARP_MIN + DIRECT_WARPS + 1)));
             CU(cudaMalloc(&c->d_region, sizeof(int) * REGION_WORDS * B));
         }
         else
@@ -203,8 +203,11 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
     if(pipe == 2)
     {
         DirectParams dp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_trec, c->d_tex, c->tw, c->th, c->d_keys, c->d_hiz, c->d_parked, c->d_far_count, c->d_region, c->d_vstat,
-                            c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->ntri, c->nuniq, c->xres, c->yres, c->hbx, c->hby, n };
-        const int tris_per_cta = DIRECT_WARPS * DIRECT_TRIS_PER_WARP;
+                            c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->ntri, c->nuniq, c->xres, c->yres, c->hbx, c->hby, n, DIRECT_TRIS_PER_WARP };
+        /* a warp streams 1024 consecutive triangles; small batches (few views, small meshes) take shorter runs so that the
+         * grid still has a few warps for every warp slot of the machine */
+        while(dp.tpw > DIRECT_TRIS_PER_WARP_MIN && (long long) ((c->ntri + dp.tpw - 1) / dp.tpw) * n < 3LL * c->num_sms * 32) dp.tpw >>= 1;
+        const int tris_per_cta = DIRECT_WARPS * dp.tpw;
         const dim3 rgrid((c->ntri + tris_per_cta - 1) / tris_per_cta, n);
         direct_clear_kernel<<<dim3(64, n), 256, 0, s>>>(dp);
         c->stats.kernels_launched++;
