@@ -75,6 +75,9 @@ def main():
                     # oracle for every fragment that passed the depth test when it was drawn -- a subset
                     fl = int(r.stats()["flags"])
                     ok = ok and (fl & 1) == (int(ref["clipped"]) & 1) and (fl & 2) <= (int(ref["clipped"]) & 2) and (out["rc"] != 0) == (fl != 0)
+                    if ok and rep == 1:                                                                      # and without checksums (the other variants of the kernels)
+                        plain = r.render(bases, z=True)
+                        ok = np.array_equal(plain["pixel"], ref["pixel"]) and np.array_equal(plain["z"].view(np.uint32), ref["z"].view(np.uint32))
                     if not ok:
                         bad += 1
                         print(f"seed {seed} pipeline {pl} rep {rep} res {res} tris {tv.shape[0]}: MISMATCH pixels {(out['pixel'] != ref['pixel']).sum()} "

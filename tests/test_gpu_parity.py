@@ -46,6 +46,8 @@ def assert_views_match(r, tv, tn, tt, tex, bases, *, expect_rc=0):
     assert bad == 0, f"{bad} pixels differ"
     assert np.array_equal(bits(out["z"]), bits(ref["z"]))
     assert np.array_equal(out["hash"], ref["hash"])
+    plain = r.render(bases, pixels=True, z=True)                        # without checksums: the other variants of the kernels
+    assert np.array_equal(plain["pixel"], ref["pixel"]) and np.array_equal(bits(plain["z"]), bits(ref["z"]))
     return out, ref
 
 
