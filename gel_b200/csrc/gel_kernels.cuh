@@ -166,9 +166,21 @@ batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint3
 /* K2: setup + binning                                                                              */
 /* ------------------------------------------------------------------------------------------------ */
 
+/* Per-(view, triangle) record K2 leaves for the rasteriser: everything of tbarycenter / tdraw that depends on the triangle
+ * and the view but not on the pixel (main.c:319-324, 344-347), computed ONCE here -- where the three corners are loaded anyway
+ * for the bbox -- instead of once per (triangle, tile) in the visibility pass and once per lit PIXEL in the shade pass.
+ * 8 x 16 bytes = one 128-byte line per triangle, so whatever part a consumer needs arrives with one L2 request:
+ *   0  ax, ay, v0x, v0y            1  v1x, v1y, k0, k1           2  d00, d01, d11, den (sign-normalised, den > 0)
+ *   3  az, bz, cz, ~tri            4  bbox x0 | x1 << 16, y0 | y1 << 16 (clipped to the frame), flags (1 drawable, 2 guard), zmax
+ *   5  shade a, b, c, -            6  ta.x, ta.y, tb.x, tb.y     7  tc.x, tc.y, -, -
+ * Same operations on the same operands as before (gel::tri_setup), so the frames do not change by a bit. */
+constexpr int VREC_QUADS = 8;
+
 struct BinParams
 {
     const float4* xf; const uint32_t *i0, *i1, *i2;
+    const float2* uv;    /* [3 * ntri] texture coordinates (copied into the records)                       */
+    float4* vrec;        /* [view][ntri][VREC_QUADS]  per-view triangle records (null: not wanted)         */
     uint32_t* entries;   /* [view][cap_e]   triangle index                                                */
     uint4* descs;        /* [view][cap_d]   (next desc or -1, first entry, entry count, chunk)            */
     int* heads;          /* [view][ntiles][NCHAIN]  top of each chain, -1 = empty                         */
@@ -224,6 +236,25 @@ bin_kernel(BinParams p)
             {
                 clipped = true;            /* the reference writes out of bounds here */
                 x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, p.xres - 1); y1 = min(y1, p.yres - 1);
+            }
+            if(p.vrec)
+            {
+                const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+                const float ad = fabsf(s.den);
+                const bool drawable = ad > 0.0f && x0 <= x1 && y0 <= y1;   /* den == 0 or NaN can never pass main.c:352 */
+                const float sg = s.den < 0.0f ? -1.0f : 1.0f;              /* exact sign flips */
+                const float2 ta = __ldg(p.uv + 3 * (size_t) t), tb = __ldg(p.uv + 3 * (size_t) t + 1), tc = __ldg(p.uv + 3 * (size_t) t + 2);
+                const uint32_t bx = (uint32_t) (x0 & 0xFFFF) | (uint32_t) (x1 & 0xFFFF) << 16, by = (uint32_t) (y0 & 0xFFFF) | (uint32_t) (y1 & 0xFFFF) << 16;
+                float4* r = p.vrec + ((size_t) view * p.ntri + t) * VREC_QUADS;
+                r[0] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
+                r[1] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
+                r[2] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
+                r[3] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - (uint32_t) t));
+                r[4] = make_float4(__uint_as_float(bx), __uint_as_float(by), __uint_as_float((drawable ? 1u : 0u) | (ad <= GUARD_DEN_MAX ? 2u : 0u)),
+                                   fmaxf(a.z, fmaxf(b.z, c.z)));
+                r[5] = make_float4(a.w, b.w, c.w, 0.0f);
+                r[6] = make_float4(ta.x, ta.y, tb.x, tb.y);
+                r[7] = make_float4(tc.x, tc.y, 0.0f, 0.0f);
             }
             if(x0 <= x1 && y0 <= y1)
             {
@@ -355,7 +386,7 @@ bin_kernel(BinParams p)
 
 struct RasterParams
 {
-    const float4* xf; const uint32_t *i0, *i1, *i2; const float2* uv;
+    const float4* vrec;   /* [view][ntri][VREC_QUADS] from K2 */
     const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list; const int* tile_lit;
     const uint32_t* vstat; uint4* far_scratch;
     const uint32_t* tex; int tw, th;
@@ -376,7 +407,7 @@ struct WarpScratch
 
 struct RasterSmem
 {
-    unsigned long long keys[TW * TH];   /* 8 KB  depth+winner per pixel, index x_local*TH + y_local */
+    unsigned long long keys[TW * TH];   /* 8 KB  depth+winner per pixel, index key_slot(x_local, y_local) */
     WarpScratch ws[RASTER_WARPS];
     int seg_first[SEG_SLOTS];
     int seg_pre[SEG_SLOTS];             /* exclusive prefix of the staged segment sizes */
@@ -397,24 +428,17 @@ struct RasterSmem
  *   q0 = ax, ay, v0x, v0y      q1 = v1x, v1y, k0, k1      q2 = d00, d01, d11, den (> 0)      q3 = az, bz, cz, ~tri */
 struct TriRecord { float4 q0, q1, q2, q3; uint32_t bbox; int npx; };
 
-/* loads triangle `tri` of the view, runs the per-triangle part of tbarycenter/tdraw (main.c:319-324, 344-347)
- * and clips its bbox to the tile */
-__device__ __forceinline__ TriRecord make_record(const float4& a, const float4& b, const float4& c, uint32_t tri, int px0, int py0, int px1, int py1)
+/* triangle record of the view (from K2) with its bbox clipped to the tile; r4 = quad 4 of the record (already loaded by the
+ * caller for the near / far decision) */
+__device__ __forceinline__ TriRecord load_record(const float4* __restrict__ rec, const float4& r4, int px0, int py0, int px1, int py1)
 {
-    const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
-    const int bx0 = max(s.x0, px0) - px0, bx1 = min(s.x1, px1) - px0;
-    const int by0 = max(s.y0, py0) - py0, by1 = min(s.y1, py1) - py0;
-    const float ad = fabsf(s.den);
-    const bool drawable = ad > 0.0f;                      /* den == 0 or NaN can never pass main.c:352 */
-    const bool guard = ad <= GUARD_DEN_MAX;
-    const float sg = s.den < 0.0f ? -1.0f : 1.0f;         /* exact sign flips */
+    const uint32_t bx = __float_as_uint(r4.x), by = __float_as_uint(r4.y), fl = __float_as_uint(r4.z);
+    const int bx0 = max((int) (bx & 0xFFFF), px0) - px0, bx1 = min((int) (bx >> 16), px1) - px0;
+    const int by0 = max((int) (by & 0xFFFF), py0) - py0, by1 = min((int) (by >> 16), py1) - py0;
     TriRecord r;
-    r.npx = (bx0 <= bx1 && by0 <= by1 && drawable) ? (bx1 - bx0 + 1) * (by1 - by0 + 1) : 0;
-    r.q0 = make_float4(s.ax, s.ay, s.v0x, s.v0y);
-    r.q1 = make_float4(s.v1x, s.v1y, s.k0, s.k1);
-    r.q2 = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
-    r.q3 = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
-    r.bbox = (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15 | (guard ? 1u << 20 : 0u);
+    r.npx = (bx0 <= bx1 && by0 <= by1 && (fl & 1u)) ? (bx1 - bx0 + 1) * (by1 - by0 + 1) : 0;
+    r.q0 = __ldg(rec); r.q1 = __ldg(rec + 1); r.q2 = __ldg(rec + 2); r.q3 = __ldg(rec + 3);
+    r.bbox = (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15 | ((fl & 2u) ? 1u << 20 : 0u);
     return r;
 }
 
@@ -424,11 +448,12 @@ __device__ __forceinline__ TriRecord make_record(const float4& a, const float4& 
  * key over its pixels, and a far triangle whose every fragment is provably below that -- z <= zmax*(1+7ulp)
  * < bound, and bound < the minimum of every block its bbox touches, strictly -- can never pass main.c:356
  * and is dropped without being set up. */
-__device__ __forceinline__ uint32_t clipped_bbox(const float4& a, const float4& b, const float4& c, int px0, int py0, int px1, int py1, bool& any)
+__device__ __forceinline__ uint32_t clipped_bbox(const float4& r4, int px0, int py0, int px1, int py1, bool& any)
 {
-    const int bx0 = max(gel::trunc_i(fminf(a.x, fminf(b.x, c.x))), px0) - px0, bx1 = min(gel::trunc_i(fmaxf(a.x, fmaxf(b.x, c.x))), px1) - px0;
-    const int by0 = max(gel::trunc_i(fminf(a.y, fminf(b.y, c.y))), py0) - py0, by1 = min(gel::trunc_i(fmaxf(a.y, fmaxf(b.y, c.y))), py1) - py0;
-    any = bx0 <= bx1 && by0 <= by1;
+    const uint32_t bx = __float_as_uint(r4.x), by = __float_as_uint(r4.y), fl = __float_as_uint(r4.z);
+    const int bx0 = max((int) (bx & 0xFFFF), px0) - px0, bx1 = min((int) (bx >> 16), px1) - px0;
+    const int by0 = max((int) (by & 0xFFFF), py0) - py0, by1 = min((int) (by >> 16), py1) - py0;
+    any = bx0 <= bx1 && by0 <= by1 && (fl & 1u);           /* a triangle that cannot draw (den == 0 / NaN, empty bbox) is not worth parking */
     return (uint32_t) (bx0 & 31) | (uint32_t) (bx1 & 31) << 5 | (uint32_t) (by0 & 31) << 10 | (uint32_t) (by1 & 31) << 15;
 }
 
@@ -466,6 +491,18 @@ __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, f
     return ((unsigned long long) gel::zkey(z) << 32) | __float_as_uint(q3.w);
 }
 
+/* Where pixel (x_local, y_local) of the tile keeps its key.  Column x owns the 32 slots [x*TH, x*TH + 32) -- a warp walking a
+ * column (shade pass, hi-Z) touches every bank once -- but inside the column the rows are ROTATED by 8*(x&3) + (x>>2): the
+ * survivors a warp resolves together mostly sit on the same row of neighbouring columns (the unit path walks the columns of a
+ * triangle in lock step), and with the plain x*TH + y layout all of those fall on one bank pair (an 11-way conflict for an
+ * 11-column triangle; 32 % of the kernel's shared-memory wavefronts were conflicts).  The rotation sends the 32 columns of one
+ * row to 32 different slots modulo 32, and the four columns of a 4x8 sweep patch to four disjoint groups of eight. */
+#ifndef GEL_KEY_SWIZZLE
+#define GEL_KEY_SWIZZLE 1
+#endif
+__device__ __forceinline__ int key_slot(int xl, int yl) { return GEL_KEY_SWIZZLE ? xl * TH + ((yl + 8 * (xl & 3) + (xl >> 2)) & 31) : xl * TH + yl; }
+__device__ __forceinline__ int key_slot_id(uint32_t id) { return key_slot((int) ((id >> 5) & 31), (int) (id & 31)); }
+
 /* stage 2 of the small path: one survivor per lane */
 __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws, int i)
 {
@@ -473,7 +510,7 @@ __device__ __forceinline__ void resolve_survivor(RasterSmem& sm, WarpScratch& ws
     const float2 n = ws.q_n[i];
     const int src = id >> 10;
     const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
-    unsigned long long* k = sm.keys + (id & 1023);           /* x_local*TH + y_local */
+    unsigned long long* k = sm.keys + key_slot_id(id);
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
 
@@ -486,7 +523,7 @@ __device__ __forceinline__ void resolve_swept(RasterSmem& sm, WarpScratch& ws, i
     const float2 n = ws.q_n[i];
     const int src = id >> 10;
     const unsigned long long key = fragment_key(n.x, n.y, sm.dslab[2][src].w, sm.dslab[3][src]);
-    unsigned long long* k = sm.keys + (id & 1023);
+    unsigned long long* k = sm.keys + key_slot_id(id);
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
 
@@ -598,10 +635,11 @@ raster_kernel(RasterParams p)
         const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
         uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
         float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
-        const float4* xf = p.xf + (size_t) view * p.nuniq;
+        const float4* __restrict__ vrec = p.vrec + (size_t) view * p.ntri * VREC_QUADS;
         const uint4* descs = p.descs + (size_t) view * p.cap_d;
         const uint32_t* entries = p.entries + (size_t) view * p.cap_e;
         unsigned long long hp = 0, hz = 0;
+        const float twm1 = gel::i2f(p.tw - 1), thm1 = gel::i2f(p.th - 1);   /* (float) (w - 1), (float) (h - 1) of main.c:360-361 */
 
         if(tid == 0)
         {
@@ -618,12 +656,12 @@ raster_kernel(RasterParams p)
         /* One warp, 32 candidate triangles (have / tri / a,b,c per lane) -> column units -> rows -> survivors -> keys.
          * Triangles too large for the unit path are left in sm.defer for the CTA-wide sweep. */
         int qn = 0;                                                       /* survivors on the warp's stack (warp-uniform) */
-        auto rasterise_batch = [&](bool have, uint32_t tri, const float4& a, const float4& b, const float4& c)
+        auto rasterise_batch = [&](bool have, uint32_t tri, const float4& r4)
         {
             int nun = 0, x = 0;
             if(have)
             {
-                const TriRecord r = make_record(a, b, c, tri, px0, py0, px1, py1);
+                const TriRecord r = load_record(vrec + (size_t) tri * VREC_QUADS, r4, px0, py0, px1, py1);
                 bool unitised = r.npx > 0;
                 if(r.npx > FRAG_MAX)
                 {
@@ -823,7 +861,7 @@ raster_kernel(RasterParams p)
                     const int e = e0 + lane;
                     bool have = false, park = false;
                     uint32_t tri = 0, bbox = 0, bound = 0;
-                    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+                    float4 r4 = make_float4(0, 0, 0, 0);
                     if(lane < grab && e < round_entries)
                     {
                         /* staged segment holding entry e: last slot with seg_pre <= e */
@@ -831,13 +869,13 @@ raster_kernel(RasterParams p)
                         #pragma unroll
                         for(int step = SEG_SLOTS / 2; step; step >>= 1) if(sm.seg_pre[lo + step] <= e) lo += step;
                         tri = __ldg(entries + sm.seg_first[lo] + (e - sm.seg_pre[lo]));
-                        a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
-                        const float zmax = fmaxf(a.z, fmaxf(b.z, c.z));
+                        r4 = __ldg(vrec + (size_t) tri * VREC_QUADS + 4);
+                        const float zmax = r4.w;
                         have = true;
                         if(zmax < zthr)                                   /* NaN compares false: near */
                         {
                             bool any;
-                            bbox = clipped_bbox(a, b, c, px0, py0, px1, py1, any);
+                            bbox = clipped_bbox(r4, px0, py0, px1, py1, any);
                             bound = depth_bound_key(zmax);
                             park = any; have = false;
                         }
@@ -855,7 +893,7 @@ raster_kernel(RasterParams p)
                             else have = true;                             /* scratch full: rasterise it now */
                         }
                     }
-                    rasterise_batch(have, tri, a, b, c);
+                    rasterise_batch(have, tri, r4);
                 }
             }
             __syncthreads();
@@ -871,7 +909,7 @@ raster_kernel(RasterParams p)
             /* hiz: a warp reads column x (lane = row); block = (x/8)*4 + lane/8 */
             for(int x = warp; x < TW; x += RASTER_WARPS)
             {
-                uint32_t zk = (uint32_t) (sm.keys[x * TH + lane] >> 32);
+                uint32_t zk = (uint32_t) (sm.keys[key_slot(x, lane)] >> 32);
                 zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 1));
                 zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 2));
                 zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 4));
@@ -889,18 +927,18 @@ raster_kernel(RasterParams p)
                     const int e = e0 + lane;
                     bool have = false;
                     uint32_t tri = 0;
-                    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+                    float4 r4 = make_float4(0, 0, 0, 0);
                     if(e < nfar)
                     {
                         const uint4 rec = far_rec[e];
                         if(survives_hiz(sm, rec.y, rec.z))
                         {
                             tri = rec.x;
-                            a = __ldg(xf + __ldg(p.i0 + tri)); b = __ldg(xf + __ldg(p.i1 + tri)); c = __ldg(xf + __ldg(p.i2 + tri));
+                            r4 = __ldg(vrec + (size_t) tri * VREC_QUADS + 4);
                             have = true;
                         }
                     }
-                    if(__any_sync(0xFFFFFFFFu, have)) rasterise_batch(have, tri, a, b, c);
+                    if(__any_sync(0xFFFFFFFFu, have)) rasterise_batch(have, tri, r4);
                 }
             }
             __syncthreads();
@@ -914,24 +952,27 @@ raster_kernel(RasterParams p)
         {
             const int x = px0 + (i >> 5), y = py0 + (i & 31);
             if(x > px1 || y > py1) continue;
-            const unsigned long long key = sm.keys[i];
+            const unsigned long long key = sm.keys[key_slot(i >> 5, i & 31)];
             uint32_t colour = 0u;
             float z = -FLT_MAX;
             if(key != CLEAR_KEY)
             {
                 const uint32_t tri = 0xFFFFFFFFu - (uint32_t) key;
                 z = gel::zkey_inv((uint32_t) (key >> 32));
-                const float4 a = __ldg(xf + __ldg(p.i0 + tri));
-                const float4 b = __ldg(xf + __ldg(p.i1 + tri));
-                const float4 c = __ldg(xf + __ldg(p.i2 + tri));
-                const gel::TriSetup s = gel::tri_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
-                float nv, nw, v, w, u, zz;
-                gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), nv, nw);
-                gel::bary_inside(s, nv, nw, v, w, u, zz);
-                const float2 ta = __ldg(p.uv + 3 * (size_t) tri), tb = __ldg(p.uv + 3 * (size_t) tri + 1), tc = __ldg(p.uv + 3 * (size_t) tri + 2);
-                const float uv[6] = { ta.x, ta.y, tb.x, tb.y, tc.x, tc.y };
+                /* tbarycenter at this pixel (main.c:316-332) from the triangle's record: the operations and operands of the
+                 * visibility pass, so v, w, u are the bits that passed the inside test there */
+                const float4* __restrict__ rec = vrec + (size_t) tri * VREC_QUADS;
+                const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), sh = __ldg(rec + 5), t0 = __ldg(rec + 6), t1 = __ldg(rec + 7);
+                const float v2x = gel::sub(gel::i2f(x), q0.x), v2y = gel::sub(gel::i2f(y), q0.y);
+                const float d20 = gel::add(gel::add(gel::mul(v2x, q0.z), gel::mul(v2y, q0.w)), q1.z);
+                const float d21 = gel::add(gel::add(gel::mul(v2x, q1.x), gel::mul(v2y, q1.y)), q1.w);
+                const float nv = gel::sub(gel::mul(q2.z, d20), gel::mul(q2.y, d21));
+                const float nw = gel::sub(gel::mul(q2.x, d21), gel::mul(q2.y, d20));
+                const float v = gel::dvd(nv, q2.w), w = gel::dvd(nw, q2.w);
+                const float u = gel::sub(gel::sub(1.0f, v), w);
+                const float uv[6] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y };
                 int xx, yy, shading;
-                gel::fragment_shade(v, w, u, uv, a.w, b.w, c.w, p.tw, p.th, xx, yy, shading);
+                gel::fragment_shade_f(v, w, u, uv, sh.x, sh.y, sh.z, twm1, thm1, xx, yy, shading);
                 if(xx < 0 || xx > p.tw - 1 || yy < 0 || yy > p.th - 1)
                 {
                     atomicOr(p.flags + view, FLAG_TEXCLAMP);   /* the reference reads out of bounds here (R) */

@@ -58,7 +58,7 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 1024 / RASTER_THREADS, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr;
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr; float4* d_vrec = nullptr;   /* d_vrec: per-(view, triangle) records K2 leaves for K3 */
     /* direct pipeline */
     unsigned long long* d_keys = nullptr; uint32_t* d_hiz = nullptr; uint4* d_parked = nullptr; int *d_far_count = nullptr, *d_region = nullptr; int hbx = 0, hby = 0;
     int pipeline_opt = 0, pipeline_auto = 1, work_pipeline = 0;   /* 0 auto, 1 tile, 2 direct */
@@ -90,7 +90,7 @@ void free_bins(gelcu_ctx* c)
 void free_work(gelcu_ctx* c)
 {
     free_bins(c);
-    dfree(c->d_xf); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
+    dfree(c->d_xf); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_vrec); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]); dfree(c->d_rgb[0]); dfree(c->d_rgb[1]);
     c->batch = 0;
@@ -110,7 +110,7 @@ size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
     const size_t frame = (size_t) c->xres * c->yres;
     size_t b = 2 * frame * 8 + (size_t) c->nuniq * 16 + 64;
     if(active_pipeline(c) == 2) b += frame * 8 + (size_t) c->hbx * c->hby * 4 + (size_t) c->ntri * 16;
-    else b += (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * (NCHAIN + 2) * 4;
+    else b += (size_t) cap_e * 4 + (size_t) cap_d * 16 + (size_t) c->ntiles * (NCHAIN + 2) * 4 + (size_t) c->ntri * VREC_QUADS * 16;
     return b;
 }
 
@@ -145,6 +145,7 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
             CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
             CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
             CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+            CU(cudaMalloc(&c->d_vrec, sizeof(float4) * VREC_QUADS * std::max<size_t>(1, (size_t) B * c->ntri)));
         }
         for(int k = 0; k < 2; k++)
         {
@@ -289,13 +290,13 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
     {
         if(c->ntri > 0)
         {
-            BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
+            BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_vrec, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
                              c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d };
             bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
             c->stats.kernels_launched++;
         }
         if(ev) CU(cudaEventRecord(ev[2], s));
-        RasterParams rp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_vstat, c->d_far,
+        RasterParams rp = { c->d_vrec, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_vstat, c->d_far,
                             c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
                             c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
         const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
