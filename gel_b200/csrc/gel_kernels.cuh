@@ -45,16 +45,25 @@ constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 #ifndef GEL_ZSPLIT_TILE
 #define GEL_ZSPLIT_TILE 0.4f          /* near / far split of a view as a fraction of its depth range: a speed heuristic, any value is exact */
 #endif
+#ifndef GEL_UNIT_WINDOW
+#define GEL_UNIT_WINDOW 256
+#endif
+#ifndef GEL_DEFER_MAX
+#define GEL_DEFER_MAX 48
+#endif
+#ifndef GEL_RASTER_MINB
+#define GEL_RASTER_MINB 8          /* resident rasteriser CTAs per SM the kernel is compiled for (registers) and its shared memory is sized for */
+#endif
 #ifndef GEL_TWO_PHASE_MIN
 #define GEL_TWO_PHASE_MIN 8
 #endif
 constexpr int FRAG_MAX = GEL_FRAG_MAX;      /* bbox-in-tile pixels up to which a triangle goes through the per-warp unit path */
-constexpr int UNIT_WINDOW = 256;   /* column units (one bbox column of one triangle) staged per warp per pass */
+constexpr int UNIT_WINDOW = GEL_UNIT_WINDOW;   /* column units (one bbox column of one triangle) staged per warp per pass */
 constexpr int QCAP = 64;           /* survivor stack per warp: < 32 left over + one row of 32 lanes       */
 constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16 B each, global scratch)   */
 constexpr int TWO_PHASE_MIN = GEL_TWO_PHASE_MIN;  /* tiles with fewer entries are rasterised in one phase                */
-constexpr int MAX_BATCH = 256;     /* views per launch set (K3 keeps a per-view prefix in shared memory)  */
-constexpr int DEFER_MAX = 48;      /* large triangles per round left to the CTA-wide sweep (their setup records wait in shared memory) */
+constexpr int MAX_BATCH = 256;     /* views per launch set (the work list packs the view in 8 bits)         */
+constexpr int DEFER_MAX = GEL_DEFER_MAX;      /* large triangles per round left to the CTA-wide sweep (their setup records wait in shared memory) */
 constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
 constexpr int SEG_SLOTS = RASTER_THREADS;   /* segments staged per round (one per thread)                 */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
@@ -155,7 +164,7 @@ batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint3
     }
     if(heads)
     {
-        if(i0 < 2) work[i0] = 0;
+        if(i0 < 3) work[i0] = 0;
         const size_t nlit = (size_t) nviews * ntiles, nheads = nlit * NCHAIN;
         for(size_t i = i0; i < nheads; i += stride) heads[i] = -1;
         for(size_t i = i0; i < nlit; i += stride) tile_lit[i] = 0;
@@ -186,7 +195,8 @@ struct BinParams
     int* heads;          /* [view][ntiles][NCHAIN]  top of each chain, -1 = empty                         */
     int* cursors;        /* [view][4]       entries used, descs used (both keep counting past the capacity), lit tiles, - */
     int* tile_lit;       /* [view][ntiles]  1 once a segment was published for the tile                           */
-    int* lit_list;       /* [view][ntiles]  the lit tiles, in publication order                                   */
+    uint32_t* lit_list;  /* [nviews * ntiles]  the batch's lit tiles (view << 24 | tile) in publication order: K3's work list */
+    int* work;           /* [2] = number of lit tiles published                                                          */
     uint32_t* flags;     /* [view]                                                                        */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d;
 };
@@ -197,15 +207,19 @@ __device__ __forceinline__ void publish_segment(const BinParams& p, int view, in
     const int prev = atomicExch(head, id);
     p.descs[(size_t) view * p.cap_d + id] = make_uint4((uint32_t) prev, (uint32_t) first, (uint32_t) count, (uint32_t) chunk);
     if(prev < 0 && atomicExch(p.tile_lit + (size_t) view * p.ntiles + tile, 1) == 0)
-        p.lit_list[(size_t) view * p.ntiles + atomicAdd(p.cursors + 4 * view + 2, 1)] = tile;
+        p.lit_list[atomicAdd(p.work + 2, 1)] = (uint32_t) view << 24 | (uint32_t) tile;
 }
 
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_kernel(BinParams p)
 {
-    __shared__ int s_cnt[LOCAL_MAX];     /* pairs per local tile slot                         */
-    __shared__ int s_pre[LOCAL_MAX];     /* exclusive prefix: entries | segments << 20        */
-    __shared__ int s_fil[LOCAL_MAX];     /* placement cursor per slot                         */
+    /* one buffer, two lives: first the warps' record staging slabs (4.5 KB each), then -- after the barrier that follows the
+     * triangle loop -- the three grouping arrays */
+    __shared__ float4 s_rec[BIN_THREADS / 32][32 * (VREC_QUADS + 1)];
+    static_assert(sizeof(float4) * (BIN_THREADS / 32) * 32 * (VREC_QUADS + 1) >= 3 * sizeof(int) * LOCAL_MAX, "the grouping arrays alias the staging slabs");
+    int* const s_cnt = reinterpret_cast<int*>(&s_rec[0][0]);   /* [LOCAL_MAX] pairs per local tile slot                  */
+    int* const s_pre = s_cnt + LOCAL_MAX;                      /* [LOCAL_MAX] exclusive prefix: entries | segments << 20 */
+    int* const s_fil = s_pre + LOCAL_MAX;                      /* [LOCAL_MAX] placement cursor per slot                  */
     __shared__ int s_rect[4];            /* CTA bounding tile rect of its normal triangles    */
     __shared__ int s_warp[BIN_THREADS / 32];
     __shared__ int s_ebase, s_dbase, s_ok;
@@ -245,7 +259,9 @@ bin_kernel(BinParams p)
                 const float sg = s.den < 0.0f ? -1.0f : 1.0f;              /* exact sign flips */
                 const float2 ta = __ldg(p.uv + 3 * (size_t) t), tb = __ldg(p.uv + 3 * (size_t) t + 1), tc = __ldg(p.uv + 3 * (size_t) t + 2);
                 const uint32_t bx = (uint32_t) (x0 & 0xFFFF) | (uint32_t) (x1 & 0xFFFF) << 16, by = (uint32_t) (y0 & 0xFFFF) | (uint32_t) (y1 & 0xFFFF) << 16;
-                float4* r = p.vrec + ((size_t) view * p.ntri + t) * VREC_QUADS;
+                /* the record goes through the warp's staging slab (stride 9 quads: conflict-free) so that the warp writes its 32
+                 * consecutive records as eight fully coalesced 512-byte stores instead of 256 scattered 16-byte ones */
+                float4* r = s_rec[warp] + lane * (VREC_QUADS + 1);
                 r[0] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
                 r[1] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
                 r[2] = make_float4(s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg);
@@ -264,6 +280,21 @@ bin_kernel(BinParams p)
                 if((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= HUGE_TILES)
                 { minx = min(minx, tx0); miny = min(miny, ty0); maxx = max(maxx, tx1); maxy = max(maxy, ty1); }
             }
+        }
+        if(p.vrec)
+        {
+            /* the warp's records of this round: triangles [t0, t0 + 32) below ntri */
+            __syncwarp();
+            const int t0 = chunk * BIN_CHUNK + k * BIN_THREADS + warp * 32;
+            const int nrec = min(32, p.ntri - t0);
+            float4* dst = p.vrec + ((size_t) view * p.ntri + t0) * VREC_QUADS;
+            #pragma unroll
+            for(int j = 0; j < VREC_QUADS; j++)
+            {
+                const int q = j * 32 + lane;
+                if((q >> 3) < nrec) dst[q] = s_rec[warp][(q >> 3) * (VREC_QUADS + 1) + (q & 7)];
+            }
+            __syncwarp();
         }
     }
     if(__any_sync(0xFFFFFFFFu, clipped) && lane == 0) atomicOr(p.flags + view, FLAG_CLIPPED);
@@ -387,10 +418,10 @@ bin_kernel(BinParams p)
 struct RasterParams
 {
     const float4* vrec;   /* [view][ntri][VREC_QUADS] from K2 */
-    const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const int* lit_list; const int* tile_lit;
+    const uint32_t* entries; const uint4* descs; const int* heads; const int* cursors; const uint32_t* lit_list; const int* tile_lit;
     const uint32_t* vstat; uint4* far_scratch;
     const uint32_t* tex; int tw, th;
-    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;   /* [0] lit-tile queue, [1] reset queue */
+    uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;   /* [0] lit-tile queue, [1] reset queue, [2] lit tiles published by K2 */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
 };
 
@@ -413,7 +444,6 @@ struct RasterSmem
     int seg_pre[SEG_SLOTS];             /* exclusive prefix of the staged segment sizes */
     float4 dslab[4][DEFER_MAX];         /* setup records (q0..q3 of the slab layout) of the triangles left to the CTA-wide sweep */
     uint32_t dbbox[DEFER_MAX];
-    int view_pre[MAX_BATCH + 1];        /* exclusive prefix of the views' lit-tile counts */
     int chain[NCHAIN];
     int warp_sums[RASTER_WARPS];
     unsigned long long hash[2];
@@ -572,7 +602,7 @@ __device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int 
 }
 
 template<bool HASH>
-__global__ void __launch_bounds__(RASTER_THREADS, 1024 / RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, GEL_RASTER_MINB)
 raster_kernel(RasterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -581,23 +611,8 @@ raster_kernel(RasterParams p)
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpScratch& ws = sm.ws[warp];
 
-    /* work list = the lit tiles of every view, view-major: prefix of the per-view counts K2 left in cursors[view][2] */
-    if(warp == 0)
-    {
-        int run = 0;
-        for(int base = 0; base < MAX_BATCH; base += 32)
-        {
-            const int v = base + lane;
-            const int c = v < p.nviews ? __ldg(p.cursors + 4 * v + 2) : 0;
-            int incl = c;
-            for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if(lane >= d) incl += n; }
-            sm.view_pre[v] = run + incl - c;
-            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-        if(lane == 0) sm.view_pre[MAX_BATCH] = run;
-    }
-    __syncthreads();
-    const int nitems = sm.view_pre[MAX_BATCH];
+    /* work list = the lit tiles of the whole batch as K2 published them (view << 24 | tile) */
+    const int nitems = __ldg(p.work_counter + 2);
 
     /* thread 0 owns the work queue: the atomic for the NEXT item is issued when the current tile starts and its
      * result is only consumed after the tile's visibility pass, so the round trip hides behind real work */
@@ -607,11 +622,8 @@ raster_kernel(RasterParams p)
         nx_view = -1;
         if(g < nitems)
         {
-            int lo = 0;
-            #pragma unroll
-            for(int step = MAX_BATCH / 2; step; step >>= 1) if(lo + step < p.nviews && sm.view_pre[lo + step] <= g) lo += step;
-            nx_view = lo;
-            nx_tile = __ldg(p.lit_list + (size_t) lo * p.ntiles + (g - sm.view_pre[lo]));
+            const uint32_t item = __ldg(p.lit_list + g);
+            nx_view = (int) (item >> 24); nx_tile = (int) (item & 0xFFFFFFu);
         }
     };
     if(tid == 0) { locate(atomicAdd(p.work_counter, 1)); c_next = atomicAdd(p.work_counter + 1, CLEAR_CHUNK); }
@@ -907,13 +919,15 @@ raster_kernel(RasterParams p)
         if(nfar > 0)
         {
             /* hiz: a warp reads column x (lane = row); block = (x/8)*4 + lane/8 */
-            for(int x = warp; x < TW; x += RASTER_WARPS)
+            /* block column gx = the 8 pixel columns [8 gx, 8 gx + 8): a lane first takes the minimum of its row over them, then
+             * one reduction per group of 8 lanes (8 rows) gives the block's value -- no atomics, each block has one writer */
+            for(int gx = warp; gx < TW / 8; gx += RASTER_WARPS)
             {
-                uint32_t zk = (uint32_t) (sm.keys[key_slot(x, lane)] >> 32);
-                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 1));
-                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 2));
-                zk = min(zk, __shfl_xor_sync(0xFFFFFFFFu, zk, 4));
-                if((lane & 7) == 0) atomicMin(&sm.hiz[(x >> 3) * 4 + (lane >> 3)], zk);
+                uint32_t zk = 0xFFFFFFFFu;
+                #pragma unroll
+                for(int dx = 0; dx < 8; dx++) zk = min(zk, (uint32_t) (sm.keys[key_slot(gx * 8 + dx, lane)] >> 32));
+                zk = __reduce_min_sync(0xFFu << (lane & 24), zk);
+                if((lane & 7) == 0) sm.hiz[gx * 4 + (lane >> 3)] = zk;
             }
             if(tid == 0) { sm.next_entry = 0; sm.ndefer = 0; }
             __syncthreads();                                              /* hiz complete, far_rec visible to the whole CTA */

@@ -58,7 +58,7 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 1024 / RASTER_THREADS, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr, *d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr; float4* d_vrec = nullptr;   /* d_vrec: per-(view, triangle) records K2 leaves for K3 */
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr; uint32_t* d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr; float4* d_vrec = nullptr;   /* d_vrec: per-(view, triangle) records K2 leaves for K3 */
     /* direct pipeline */
     unsigned long long* d_keys = nullptr; uint32_t* d_hiz = nullptr; uint4* d_parked = nullptr; int *d_far_count = nullptr, *d_region = nullptr; int hbx = 0, hby = 0;
     int pipeline_opt = 0, pipeline_auto = 1, work_pipeline = 0;   /* 0 auto, 1 tile, 2 direct */
@@ -94,6 +94,18 @@ void free_work(gelcu_ctx* c)
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]); dfree(c->d_rgb[0]); dfree(c->d_rgb[1]);
     c->batch = 0;
+}
+
+/* Waits for everything THIS context has in flight.  Never cudaDeviceSynchronize(): a device-wide wait from one host thread is
+ * an error -- and invalidates the capture -- while another context on the same device is capturing its small-call graph in
+ * another thread ("operation not permitted when stream is capturing"). */
+cudaError_t sync_ctx(gelcu_ctx* c)
+{
+    cudaStream_t all[5] = { c->stream, c->copy_stream, c->side_stream, c->hi_stream, c->aux_stream };
+    cudaError_t first = cudaSuccess;
+    for(cudaStream_t s : all)
+        if(s) { const cudaError_t e = cudaStreamSynchronize(s); if(e != cudaSuccess && first == cudaSuccess) first = e; }
+    return first;
 }
 
 #ifndef GEL_RESOLVE_CTAS
@@ -142,9 +154,9 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
         {
             CU(cudaMalloc(&c->d_heads, sizeof(int) * (size_t) B * c->ntiles * NCHAIN));
             CU(cudaMalloc(&c->d_tile_lit, sizeof(int) * (size_t) B * c->ntiles));
-            CU(cudaMalloc(&c->d_lit_list, sizeof(int) * (size_t) B * c->ntiles));
+            CU(cudaMalloc(&c->d_lit_list, sizeof(uint32_t) * (size_t) B * c->ntiles));
             CU(cudaMalloc(&c->d_far, sizeof(uint4) * (size_t) FAR_CAP * c->num_sms * 16));   /* one scratch per resident rasteriser CTA */
-            CU(cudaMalloc(&c->d_work, 2 * sizeof(int)));
+            CU(cudaMalloc(&c->d_work, 4 * sizeof(int)));
             CU(cudaMalloc(&c->d_vrec, sizeof(float4) * VREC_QUADS * std::max<size_t>(1, (size_t) B * c->ntri)));
         }
         for(int k = 0; k < 2; k++)
@@ -290,7 +302,7 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
     {
         if(c->ntri > 0)
         {
-            BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_vrec, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_flags,
+            BinParams bp = { c->d_xf, c->d_i0, c->d_i1, c->d_i2, c->d_uv, c->d_vrec, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_tile_lit, c->d_lit_list, c->d_work, c->d_flags,
                              c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d };
             bin_kernel<<<dim3((c->ntri + BIN_CHUNK - 1) / BIN_CHUNK, n), BIN_THREADS, 0, s>>>(bp);
             c->stats.kernels_launched++;
@@ -433,7 +445,7 @@ int gelcu_set_mesh(gelcu_ctx* c, const float* tv, const float* tn, const float* 
     if(!c) return fail(GELCU_E_INVALID, "null context");
     if(ntri < 0 || (ntri > 0 && (!tv || !tn || !tt))) return fail(GELCU_E_INVALID, "bad mesh arguments");
     CU(cudaSetDevice(c->device));
-    CU(cudaDeviceSynchronize());
+    CU(sync_ctx(c));
     /* Load-time layout: the reference's soup repeats every shared corner (main.c:242-286); the transform is
      * a pure function of (position, normal), so identical corners are merged here (bitwise equality) and
      * the per-frame kernels run once per distinct corner and index it per triangle. */
@@ -533,7 +545,7 @@ int gelcu_set_mesh_indexed(gelcu_ctx* c, const float* v, int nv, const float* vt
     if(nv < 0 || nvt < 0 || nvn < 0 || nfaces < 0 || (nfaces > 0 && (!v || !vt || !vn || !faces || nv == 0 || nvt == 0 || nvn == 0)))
         return fail(GELCU_E_INVALID, "bad indexed mesh arguments");
     CU(cudaSetDevice(c->device));
-    CU(cudaDeviceSynchronize());
+    CU(sync_ctx(c));
     drop_mesh(c);
     /* staging: the OBJ arrays as they are (36 bytes per face + the vertex lines, against 108 bytes per face of soups) */
     struct Staging
@@ -599,7 +611,7 @@ int gelcu_set_texture(gelcu_ctx* c, const uint32_t* xrgb, int w, int h)
     if(!c) return fail(GELCU_E_INVALID, "null context");
     if(!xrgb || w <= 0 || h <= 0) return fail(GELCU_E_INVALID, "bad texture arguments");
     CU(cudaSetDevice(c->device));
-    CU(cudaDeviceSynchronize());
+    CU(sync_ctx(c));
     dfree(c->d_tex);
     CU(cudaMalloc(&c->d_tex, sizeof(uint32_t) * (size_t) w * h));
     CU(cudaMemcpy(c->d_tex, xrgb, sizeof(uint32_t) * (size_t) w * h, cudaMemcpyHostToDevice));
@@ -612,7 +624,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     if(!c || !name) return fail(GELCU_E_INVALID, "null argument");
     c->state_gen++;
     if(!strcmp(name, "graph_small_calls")) c->use_graph = value != 0;
-    else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); cudaDeviceSynchronize(); free_work(c); }
+    else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); sync_ctx(c); free_work(c); }
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
@@ -1003,7 +1015,7 @@ void gelcu_destroy(gelcu_ctx* c)
 {
     if(!c) return;
     cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
+    sync_ctx(c);
     free_work(c);
     dfree(c->d_vpos); dfree(c->d_vnrm); dfree(c->d_i0); dfree(c->d_i1); dfree(c->d_i2); dfree(c->d_uv); dfree(c->d_trec);
     dfree(c->d_tex); dfree(c->d_views);
