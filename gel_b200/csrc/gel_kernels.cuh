@@ -3,9 +3,11 @@
  *   K1 transform_kernel   one thread per (view, distinct corner): tviewnrm / tviewtri / tperspective / tviewport
  *                         (main.c:372-390, 302-314, 288-300); float4 in, float4 (screen x, y, z, shade) out
  *   K2 bin_kernel         triangle setup + screen-tile binning in ONE pass: a CTA takes 1024 consecutive
- *                         triangles, computes each bbox (main.c:344-347), groups the (triangle, tile) pairs by
- *                         tile in shared memory (count -> scan -> place) and publishes one SEGMENT per touched
- *                         tile: a contiguous run of entries in a per-view pool, pushed on the tile's chain
+ *                         triangles, computes each bbox (main.c:344-347) and the per-triangle part of tbarycenter
+ *                         (main.c:319-324) into one 128-byte record per (view, triangle), groups the (triangle, tile)
+ *                         pairs by tile in shared memory (count -> scan -> place) and publishes one SEGMENT per touched
+ *                         tile: a contiguous run of entries in a per-view pool, pushed on the tile's chain; lit tiles
+ *                         go on one batch-wide work list
  *   K3 raster_kernel      persistent CTAs pull (view, tile) items; the tile's depth + winner live in shared
  *                         memory as one 64-bit key per pixel.  Small triangles are expanded into FRAGMENTS
  *                         (one lane per bbox pixel, so lanes stay busy whatever the triangle sizes); large ones
@@ -25,6 +27,7 @@
 #include "gel_math.h"
 
 #include <cuda_runtime.h>
+#include <cuda.h>          /* CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link) */
 #include <climits>
 
 namespace gelk {
@@ -46,7 +49,7 @@ constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 #define GEL_ZSPLIT_TILE 0.4f          /* near / far split of a view as a fraction of its depth range: a speed heuristic, any value is exact */
 #endif
 #ifndef GEL_UNIT_WINDOW
-#define GEL_UNIT_WINDOW 256
+#define GEL_UNIT_WINDOW 128
 #endif
 #ifndef GEL_DEFER_MAX
 #define GEL_DEFER_MAX 48
@@ -64,6 +67,7 @@ constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16
 constexpr int TWO_PHASE_MIN = GEL_TWO_PHASE_MIN;  /* tiles with fewer entries are rasterised in one phase                */
 constexpr int MAX_BATCH = 256;     /* views per launch set (the work list packs the view in 8 bits)         */
 constexpr int DEFER_MAX = GEL_DEFER_MAX;      /* large triangles per round left to the CTA-wide sweep (their setup records wait in shared memory) */
+constexpr int RESET_BOX_COLS = 4;  /* tile columns one TMA tensor store resets (box = 32 rows x 4 columns = 512 bytes of pattern)  */
 constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
 constexpr int SEG_SLOTS = RASTER_THREADS;   /* segments staged per round (one per thread)                 */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
@@ -423,6 +427,8 @@ struct RasterParams
     const uint32_t* tex; int tw, th;
     uint32_t* pixel; float* zbuf; unsigned long long* hash; uint32_t* flags; int* work_counter;   /* [0] lit-tile queue, [1] reset queue, [2] lit tiles published by K2 */
     int ntri, nuniq, xres, yres, tiles_x, tiles_y, ntiles, cap_e, cap_d, nviews;
+    int tma_reset;        /* 1: untouched tiles are reset by TMA tensor stores through the two maps below */
+    alignas(64) CUtensorMap tm_pixel, tm_z;   /* the batch's frames as 3-D tensors (y, x, view) of 32-bit words, box 32 x RESET_BOX_COLS x 1 */
 };
 
 /* per-warp scratch of the small-triangle path */
@@ -438,6 +444,8 @@ struct WarpScratch
 
 struct RasterSmem
 {
+    alignas(128) uint32_t pat_pixel[TH * RESET_BOX_COLS];   /* 512 B of 0x00000000: source of the TMA stores that reset pixels */
+    alignas(128) uint32_t pat_z[TH * RESET_BOX_COLS];       /* 512 B of 0xFF7FFFFF (-FLT_MAX): the same for z                   */
     unsigned long long keys[TW * TH];   /* 8 KB  depth+winner per pixel, index key_slot(x_local, y_local) */
     WarpScratch ws[RASTER_WARPS];
     int seg_first[SEG_SLOTS];
@@ -522,15 +530,20 @@ __device__ __forceinline__ unsigned long long fragment_key(float nv, float nw, f
 }
 
 /* Where pixel (x_local, y_local) of the tile keeps its key.  Column x owns the 32 slots [x*TH, x*TH + 32) -- a warp walking a
- * column (shade pass, hi-Z) touches every bank once -- but inside the column the rows are ROTATED by 8*(x&3) + (x>>2): the
- * survivors a warp resolves together mostly sit on the same row of neighbouring columns (the unit path walks the columns of a
- * triangle in lock step), and with the plain x*TH + y layout all of those fall on one bank pair (an 11-way conflict for an
- * 11-column triangle; 32 % of the kernel's shared-memory wavefronts were conflicts).  The rotation sends the 32 columns of one
- * row to 32 different slots modulo 32, and the four columns of a 4x8 sweep patch to four disjoint groups of eight. */
+ * column (shade pass, hi-Z) touches every bank once -- but inside the column the rows are ROTATED by 8*(x&1) + (x>>1).  A 64-bit
+ * slot covers a PAIR of banks, so there are 16 bank pairs and a warp's 32 keys need two wavefronts at best.  The survivors a warp
+ * resolves together mostly sit on the same row of neighbouring columns (the unit path walks the columns of a triangle in lock
+ * step): with the plain x*TH + y layout they all fall on one bank pair (an 11-way conflict for an 11-column triangle; 32 % of
+ * the kernel's shared-memory wavefronts were conflicts).  With the rotation up to 16 neighbouring columns of one row land on 16
+ * different pairs (32 columns: each pair exactly twice), and the 4 columns x 8 rows of a sweep patch on every pair exactly twice. */
 #ifndef GEL_KEY_SWIZZLE
-#define GEL_KEY_SWIZZLE 1
+#define GEL_KEY_SWIZZLE 2
 #endif
-__device__ __forceinline__ int key_slot(int xl, int yl) { return GEL_KEY_SWIZZLE ? xl * TH + ((yl + 8 * (xl & 3) + (xl >> 2)) & 31) : xl * TH + yl; }
+__device__ __forceinline__ int key_slot(int xl, int yl)
+{
+    return GEL_KEY_SWIZZLE == 2 ? xl * TH + ((yl + 8 * (xl & 1) + (xl >> 1)) & 31)
+         : GEL_KEY_SWIZZLE == 1 ? xl * TH + ((yl + 8 * (xl & 3) + (xl >> 2)) & 31) : xl * TH + yl;
+}
 __device__ __forceinline__ int key_slot_id(uint32_t id) { return key_slot((int) ((id >> 5) & 31), (int) (id & 31)); }
 
 /* stage 2 of the small path: one survivor per lane */
@@ -558,13 +571,32 @@ __device__ __forceinline__ void resolve_swept(RasterSmem& sm, WarpScratch& ws, i
 }
 
 template<bool HASH>
-__device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int g, int lane)
+__device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int g, int lane, uint32_t pat_pixel, uint32_t pat_z)
 {
     if(g >= p.ntiles * p.nviews || __ldg(p.tile_lit + g)) return;
     const int view = g / p.ntiles, tile = g - view * p.ntiles;
     const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
     const int px0 = tx * TW, py0 = ty * TH;
     const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
+    if(!HASH && p.tma_reset)
+    {
+        /* TMA tensor stores (cp.async.bulk.tensor, SASS UTMASTG): lane k < 8 resets columns [4k, 4k + 4) of the pixel tile,
+         * lane 8 + k the same columns of the z tile -- one warp instruction issues the whole tile (16 boxes of 32 rows x 4
+         * columns, 8 KB) from two constant 512-byte patterns in shared memory; the copy unit generates the addresses and clips
+         * boxes at the frame's edges, so the reset costs the rasteriser CTAs 2 instructions per tile instead of ~250 */
+        constexpr int BOXES = TW / RESET_BOX_COLS;
+        const int col = px0 + (lane & (BOXES - 1)) * RESET_BOX_COLS;
+        if(lane < 2 * BOXES && col <= px1)
+        {
+            const bool zb = lane >= BOXES;
+            const unsigned long long tm = reinterpret_cast<unsigned long long>(zb ? &p.tm_z : &p.tm_pixel);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         :: "l"(tm), "r"(py0), "r"(col), "r"(view), "r"(zb ? pat_z : pat_pixel) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");     /* bounds the groups a thread has in flight */
+        }
+        return;
+    }
     uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
     float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
     if(!HASH && (p.yres & 3) == 0 && py1 - py0 + 1 == TH)
@@ -603,13 +635,18 @@ __device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int 
 
 template<bool HASH>
 __global__ void __launch_bounds__(RASTER_THREADS, GEL_RASTER_MINB)
-raster_kernel(RasterParams p)
+raster_kernel(const __grid_constant__ RasterParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     RasterSmem& sm = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpScratch& ws = sm.ws[warp];
+    /* the reset patterns: written once through the generic proxy, read by the TMA unit (async proxy) from then on -- the fence
+     * orders the two; the first barrier of the work loop publishes them to the whole CTA */
+    for(int i = tid; i < TH * RESET_BOX_COLS; i += RASTER_THREADS) { sm.pat_pixel[i] = 0u; sm.pat_z[i] = 0xFF7FFFFFu; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t pat_pixel = (uint32_t) __cvta_generic_to_shared(sm.pat_pixel), pat_z = (uint32_t) __cvta_generic_to_shared(sm.pat_z);
 
     /* work list = the lit tiles of the whole batch as K2 published them (view << 24 | tile) */
     const int nitems = __ldg(p.work_counter + 2);
@@ -641,7 +678,7 @@ raster_kernel(RasterParams p)
         const int view = sm.it_view;
         if(view < 0) break;
         if(tid == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, CLEAR_CHUNK); }
-        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, sm.it_clear + j, lane);
+        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, sm.it_clear + j, lane, pat_pixel, pat_z);
         const int tile = sm.it_tile;
         const int px0 = sm.it_tx * TW, py0 = sm.it_ty * TH;
         const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
@@ -1011,12 +1048,13 @@ raster_kernel(RasterParams p)
     /* no lit tile left: finish the chunk already reserved, then drain the reset queue */
     for(int base = sm.it_clear; base < nclear; )
     {
-        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, base + j, lane);
+        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, base + j, lane, pat_pixel, pat_z);
         __syncthreads();
         if(tid == 0) sm.it_clear = atomicAdd(p.work_counter + 1, CLEAR_CHUNK);
         __syncthreads();
         base = sm.it_clear;
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");               /* every tensor store this thread issued has landed */
 }
 
 } /* namespace gelk */

@@ -21,6 +21,7 @@
 #include <utility>
 #include <vector>
 #include <cfloat>
+#include <cudaTypedefs.h>   /* PFN_cuTensorMapEncodeTiled */
 
 using namespace gelk;
 
@@ -65,6 +66,7 @@ struct gelcu_ctx
     double mean_tri_px = 0.0;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
+    CUtensorMap tm_pixel[2] = {}, tm_z[2] = {}; bool tma_ok = false; int tma_reset = 1;   /* tile pipeline: the frame buffers as TMA tensors (reset of untouched tiles) */
     uint8_t* d_rgb[2] = { nullptr, nullptr };   /* frame sink: upright 24-bit frames, allocated on first use */
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; uint32_t* h_vstat = nullptr; int hcap = 0;
@@ -126,6 +128,25 @@ size_t per_view_bytes(const gelcu_ctx* c, int cap_e, int cap_d)
     return b;
 }
 
+/* A batch's frames (pixel or z: 32-bit words, index y + x*yres + view*xres*yres) as a 3-D TMA tensor (y, x, view) with boxes of
+ * 32 rows x RESET_BOX_COLS columns: what the tile rasteriser's reset stores address.  The encoder is a driver entry point
+ * fetched at run time (no link against libcuda).  Needs 16-byte row pitches: yres % 4 == 0. */
+bool make_frame_map(CUtensorMap* tm, void* base, int xres, int yres, int B)
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = []() {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }();
+    if(!encode || (yres & 3) != 0 || B < 1) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t) yres, (cuuint64_t) xres, (cuuint64_t) B };
+    const cuuint64_t strides[2] = { (cuuint64_t) yres * 4, (cuuint64_t) xres * yres * 4 };
+    const cuuint32_t box[3] = { (cuuint32_t) std::min(TH, yres), (cuuint32_t) std::min(RESET_BOX_COLS, xres), 1 }, estr[3] = { 1, 1, 1 };
+    if(box[0] != (cuuint32_t) TH || box[1] != (cuuint32_t) RESET_BOX_COLS) return false;   /* frames smaller than a box keep the store loop */
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 /* Work buffers for batches of up to B views.  They are kept between calls: a steady stream of calls with the same (or a
  * smaller) number of views allocates nothing.  A larger batch or another pipeline rebuilds everything; a bin-pool overflow
  * (tile pipeline) only replaces the two pools. */
@@ -164,6 +185,9 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
             CU(cudaMalloc(&c->d_pixel[k], sizeof(uint32_t) * B * frame));
             CU(cudaMalloc(&c->d_z[k], sizeof(float) * B * frame));
         }
+        c->tma_ok = pipe != 2;
+        for(int k = 0; k < 2 && c->tma_ok; k++)
+            c->tma_ok = make_frame_map(&c->tm_pixel[k], c->d_pixel[k], c->xres, c->yres, B) && make_frame_map(&c->tm_z[k], c->d_z[k], c->xres, c->yres, B);
         c->batch = B; c->work_pipeline = pipe; c->state_gen++;
     }
     if(pipe != 2 && !(c->cap_e >= cap_e && c->cap_d >= cap_d && c->d_entries))
@@ -311,6 +335,8 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         RasterParams rp = { c->d_vrec, c->d_entries, c->d_descs, c->d_heads, c->d_cursors, c->d_lit_list, c->d_tile_lit, c->d_vstat, c->d_far,
                             c->d_tex, c->tw, c->th, c->d_pixel[buf], c->d_z[buf], c->d_hash, c->d_flags, c->d_work,
                             c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
+        rp.tma_reset = (c->tma_ok && c->tma_reset) ? 1 : 0;
+        if(rp.tma_reset) { rp.tm_pixel = c->tm_pixel[buf]; rp.tm_z = c->tm_z[buf]; }
         const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
         if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
         else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
@@ -625,6 +651,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     c->state_gen++;
     if(!strcmp(name, "graph_small_calls")) c->use_graph = value != 0;
     else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); sync_ctx(c); free_work(c); }
+    else if(!strcmp(name, "tma_reset")) c->tma_reset = value ? 1 : 0;
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */

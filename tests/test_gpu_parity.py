@@ -212,6 +212,25 @@ def test_random_soup_odd_resolutions(res):
         assert np.array_equal(out["hash"], ref["hash"])
 
 
+@pytest.mark.parametrize("res", [(100, 68), (36, 32), (33, 36), (132, 100), (800, 600), (64, 64), (8, 4)])
+def test_tile_reset_through_tma_tensor_stores(res):
+    """The tile rasteriser resets untouched tiles with TMA tensor stores (boxes of 32 rows x 4 columns clipped by the copy unit at
+    the frame's edges) when no checksums are asked for and the row pitch allows it (yres % 4 == 0): frames whose last tile row /
+    column is partial, frames of exactly one tile, a sparse scene (most tiles untouched), several batches into both frame
+    buffers -- against the oracle, and against the store loop (option tma_reset = 0) on the same context."""
+    rng = np.random.default_rng(res[0] * 7 + res[1])
+    tv, tn, tt = random_soup(rng, 60, size=(0.01, 0.1), xr=(-0.3, 0.3), yr=(-0.2, 1.0))
+    tex = small_tex(rng, 32, 32)
+    bases = gel_b200.view_bases([(0.1 * k, 0.02 * k) for k in range(7)])
+    ref = oracle.render_views(tv, tn, tt, tex, res[0], res[1], bases, nthreads=NTHREADS, z=True)
+    with make_renderer(res[0], res[1], tv, tn, tt, tex) as r:
+        r.set_option("batch_views", 3)                                   # three batches: both frame buffers, a ragged last one
+        for tma in (1, 0, 1):
+            r.set_option("tma_reset", tma)
+            out = r.render(bases, z=True)
+            assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])), (res, tma)
+
+
 def test_ties_degenerates_and_large_triangles():
     rng = np.random.default_rng(21)
     tv, tn, tt = random_soup(rng, 300, size=(0.005, 0.05))
