@@ -11,6 +11,7 @@
  */
 #include "gel_mesh.cuh"
 #include "gel_sink.cuh"
+#include "gel_band.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -46,6 +47,10 @@ struct Rect { int x0, y0, x1, y1; bool empty() const { return x1 < x0 || y1 < y0
 
 } /* namespace */
 
+#ifndef GEL_RASTER_MODE
+#define GEL_RASTER_MODE 1
+#endif
+
 struct gelcu_ctx
 {
     int device = 0, xres = 0, yres = 0, tiles_x = 0, tiles_y = 0, ntiles = 0, num_sms = 148;
@@ -66,7 +71,7 @@ struct gelcu_ctx
     double mean_tri_px = 0.0;
     uint32_t* d_flags = nullptr; unsigned long long* d_hash = nullptr; int* d_work = nullptr;
     uint32_t* d_pixel[2] = { nullptr, nullptr }; float* d_z[2] = { nullptr, nullptr };
-    CUtensorMap tm_pixel[2] = {}, tm_z[2] = {}; bool tma_ok = false; int tma_reset = 1;   /* tile pipeline: the frame buffers as TMA tensors (reset of untouched tiles) */
+    CUtensorMap tm_pixel[2] = {}, tm_z[2] = {}; bool tma_ok = false; int tma_reset = 1, raster_mode = GEL_RASTER_MODE, band_ctas_per_sm = 1024 / RASTER_THREADS;   /* raster_mode: 0 = a CTA per tile (raster_kernel), 1 = a warp per band (raster_band_kernel) */   /* tile pipeline: the frame buffers as TMA tensors (reset of untouched tiles) */
     uint8_t* d_rgb[2] = { nullptr, nullptr };   /* frame sink: upright 24-bit frames, allocated on first use */
     gelcu_view* d_views = nullptr; int views_cap = 0;
     int* h_cursors = nullptr; uint32_t* h_flags = nullptr; uint32_t* h_vstat = nullptr; int hcap = 0;
@@ -337,9 +342,18 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
                             c->ntri, c->nuniq, c->xres, c->yres, c->tiles_x, c->tiles_y, c->ntiles, c->cap_e, c->cap_d, n };
         rp.tma_reset = (c->tma_ok && c->tma_reset) ? 1 : 0;
         if(rp.tma_reset) { rp.tm_pixel = c->tm_pixel[buf]; rp.tm_z = c->tm_z[buf]; }
-        const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
-        if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
-        else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        if(c->raster_mode == 1)
+        {
+            const int grid = c->num_sms * std::min(c->band_ctas_per_sm, 16);
+            if(want_hash) raster_band_kernel<true><<<grid, RASTER_THREADS, sizeof(BandSmem), s>>>(rp);
+            else raster_band_kernel<false><<<grid, RASTER_THREADS, sizeof(BandSmem), s>>>(rp);
+        }
+        else
+        {
+            const int grid = c->num_sms * std::min(c->ctas_per_sm, 16);
+            if(want_hash) raster_kernel<true><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+            else raster_kernel<false><<<grid, RASTER_THREADS, sizeof(RasterSmem), s>>>(rp);
+        }
         c->stats.kernels_launched++;
         if(ev) CU(cudaEventRecord(ev[3], s));
     }
@@ -426,6 +440,8 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     CU(cudaSetDevice(device));
     CU(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RasterSmem)));
     CU(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RasterSmem)));
+    CU(cudaFuncSetAttribute(raster_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(BandSmem)));
+    CU(cudaFuncSetAttribute(raster_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(BandSmem)));
     gelcu_ctx* c = new gelcu_ctx();
     c->device = device; c->xres = xres; c->yres = yres;
     c->tiles_x = (xres + TW - 1) / TW; c->tiles_y = (yres + TH - 1) / TH; c->ntiles = c->tiles_x * c->tiles_y;
@@ -435,6 +451,8 @@ int gelcu_create(gelcu_ctx** out, int device, int xres, int yres)
     int resident = 0;   /* persistent rasteriser: exactly as many CTAs as fit */
     if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, raster_kernel<false>, RASTER_THREADS, sizeof(RasterSmem)) == cudaSuccess && resident > 0)
         c->ctas_per_sm = std::min(resident, 16);
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, raster_band_kernel<false>, RASTER_THREADS, sizeof(BandSmem)) == cudaSuccess && resident > 0)
+        c->band_ctas_per_sm = std::min(resident, 16);
     cudaError_t s1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t s2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if(s2 == cudaSuccess) s2 = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
@@ -652,6 +670,7 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     if(!strcmp(name, "graph_small_calls")) c->use_graph = value != 0;
     else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); sync_ctx(c); free_work(c); }
     else if(!strcmp(name, "tma_reset")) c->tma_reset = value ? 1 : 0;
+    else if(!strcmp(name, "raster_mode")) { if(value < 0 || value > 1) return fail(GELCU_E_INVALID, "raster_mode must be 0 (a CTA per tile) or 1 (a warp per band)"); c->raster_mode = value; }
     else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
