@@ -89,14 +89,14 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
             /* no band left: finish the chunk already reserved, then drain the reset queue */
             for(int base = c0; base < nclear; )
             {
-                for(int j = 0; j < BAND_CLEAR; j++) reset_untouched_tile<HASH>(p, base + j, lane, pat_pixel, pat_z);
+                reset_untouched_tiles<HASH>(p, base, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
                 if(lane == 0) base = atomicAdd(p.work_counter + 1, BAND_CLEAR);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
             }
             break;
         }
         if(lane == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, BAND_CLEAR); }
-        for(int j = 0; j < BAND_CLEAR; j++) reset_untouched_tile<HASH>(p, c0 + j, lane, pat_pixel, pat_z);
+        reset_untouched_tiles<HASH>(p, c0, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
 
         const uint32_t item = __ldg(p.lit_list + g / BANDS);
         const int band = g % BANDS, view = (int) (item >> 24), tile = (int) (item & 0xFFFFFFu);

@@ -27,6 +27,9 @@ namespace gelk {
 #ifndef GEL_DIRECT_THREADS
 #define GEL_DIRECT_THREADS 32
 #endif
+#ifndef GEL_DIRECT_MINB
+#define GEL_DIRECT_MINB (1024 / GEL_DIRECT_THREADS)     /* resident CTAs per SM the raster kernels are compiled for */
+#endif
 constexpr int DIRECT_THREADS = GEL_DIRECT_THREADS;
 constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #ifndef GEL_HIZ_WIDE
@@ -43,6 +46,9 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #endif
 #ifndef GEL_DIRECT_TPW
 #define GEL_DIRECT_TPW 1024
+#endif
+#ifndef GEL_RESOLVE_IDX32
+#define GEL_RESOLVE_IDX32 1        /* resolve pass addressing: 0 = per-view base pointers + 32-bit offsets, 1 = one 32-bit element index per pixel, 2 = 1 with restrict bases */
 #endif
 #ifndef GEL_TRIM_ROUNDS
 #define GEL_TRIM_ROUNDS 1          /* rounds of exact bbox trimming per rasterised triangle (0 = off) */
@@ -81,7 +87,9 @@ struct DirectParams
 
 struct DirectScratch               /* per warp */
 {
-    float4 slab[4][32];
+    float4 slab[3][32];                  /* q0, q1, q2 of the current 32 triangles (gel_kernels.cuh, slab layout) */
+    float4 q3[32];                       /* az, bz, cz, ~tri */
+    float den[32];                       /* q2.w once more: with q3 all the division stage needs of a triangle (one 4-byte and one 16-byte read per survivor) */
     uint32_t unit[DIRECT_UNIT_WINDOW];   /* lane << 13 | x */
     uint32_t cand[DIRECT_CAND];          /* triangle ids */
     float2 q_n[QCAP];
@@ -196,12 +204,12 @@ __device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned l
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
     const uint32_t src = id >> 26, x = (id >> 13) & 8191u, y = id & 8191u;
-    const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
+    const unsigned long long key = fragment_key(n.x, n.y, ws.den[src], ws.q3[src]);
     if(key) key_max<HINT>(keys + (x * (uint32_t) p.yres + y), key, pol);  /* 32-bit unsigned offset inside the view's frame */
 }
 
 template<int PHASE, bool HINT>
-__global__ void __launch_bounds__(DIRECT_THREADS, 1024 / DIRECT_THREADS)
+__global__ void __launch_bounds__(DIRECT_THREADS, GEL_DIRECT_MINB)
 direct_raster_kernel(DirectParams p)
 {
     __shared__ DirectScratch scratch[DIRECT_WARPS];
@@ -339,7 +347,8 @@ direct_raster_kernel(DirectParams p)
                     ws.slab[0][lane] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
                     ws.slab[1][lane] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
                     ws.slab[2][lane] = q2;
-                    ws.slab[3][lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
+                    ws.q3[lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
+                    ws.den[lane] = q2.w;
                     ws.bx[lane] = (uint32_t) x0 | (uint32_t) x1 << 16;
                     ws.by[lane] = (uint32_t) y0 | (uint32_t) y1 << 13 | (guard ? 1u << 26 : 0u);
                     ws.den_hi[lane] = s.den * sg * U_SLACK;
@@ -421,7 +430,7 @@ direct_raster_kernel(DirectParams p)
         {
             const int src = __ffs(sm) - 1;
             sm &= sm - 1;
-            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src], q3 = ws.slab[3][src];
+            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src], q3 = ws.q3[src];
             const uint32_t xx = ws.bx[src], yy = ws.by[src];
             const int x0 = xx & 0xFFFF, x1 = xx >> 16, y0 = yy & 8191, y1 = (yy >> 13) & 8191;
             const float eps = (yy >> 26) & 1 ? -GUARD_EPS : -INFINITY;
@@ -454,7 +463,7 @@ direct_raster_kernel(DirectParams p)
 /* D5 ------------------------------------------------------------------------------------------------------------ */
 /* one pixel: the winner's barycentrics recomputed from the same operands (identical bits), shaded once */
 template<bool COMPACT>
-__device__ __forceinline__ void direct_shade(const DirectParams& p, const float4* __restrict__ xf, uint32_t* vflags, float twm1, float thm1,
+__device__ __forceinline__ void direct_shade(const DirectParams& p, const float4* __restrict__ xf, uint32_t vbase /* first vertex of the view in xf */, uint32_t* vflags, float twm1, float thm1,
                                              unsigned long long key, int x, int y, uint32_t& colour, float& z)
 {
     colour = 0u; z = -FLT_MAX;
@@ -477,9 +486,9 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, const float4
         ia = r0.x; ib = r0.y; ic = r0.z;
         uvw[0] = r1.x; uvw[1] = r1.y; uvw[2] = r1.z; uvw[3] = r1.w; uvw[4] = r2.x; uvw[5] = r2.y;
     }
-    const float4 a = __ldg(xf + ia);
-    const float4 b = __ldg(xf + ib);
-    const float4 c = __ldg(xf + ic);
+    const float4 a = __ldg(xf + (vbase + ia));
+    const float4 b = __ldg(xf + (vbase + ib));
+    const float4 c = __ldg(xf + (vbase + ic));
     /* tbarycenter at this pixel (main.c:316-332), same operations and operands as the visibility pass */
     const float v0x = gel::sub(b.x, a.x), v0y = gel::sub(b.y, a.y), v0z = gel::sub(b.z, a.z);
     const float v1x = gel::sub(c.x, a.x), v1y = gel::sub(c.y, a.y), v1z = gel::sub(c.z, a.z);
@@ -683,16 +692,45 @@ direct_resolve_kernel(DirectParams p)
     int rx0, rx1, ry0, ry1;
     if(!load_region(p, view, rx0, rx1, ry0, ry1)) return;
     unsigned long long hp = 0, hz = 0;
-    /* per-view bases and the texture extents as floats ((float) (w - 1), (float) (h - 1) of main.c:360-361: the same
-     * conversions, done once) live outside the pixel loop; inside it everything is a 32-bit offset from them */
+    uint32_t* vflags = p.flags + view;
+    const float twm1 = gel::i2f(p.tw - 1), thm1 = gel::i2f(p.th - 1);     /* (float) (w - 1), (float) (h - 1) of main.c:360-361, converted once */
+    const int nstrips = (rx1 - rx0 + 8) / 8;
+#if GEL_RESOLVE_IDX32
+    /* Addressing variant: a pixel is ONE 32-bit element index into the batch's buffers (view * frame + x * yres + y; the host keeps
+     * views-per-batch * frame and views-per-batch * distinct vertices below 2^32), scaled onto the buffer bases. */
+    const uint32_t frame = (uint32_t) p.xres * (uint32_t) p.yres;
+    const uint32_t fbase = (uint32_t) view * frame, vbase = (uint32_t) view * (uint32_t) p.nuniq;
+#if GEL_RESOLVE_IDX32 == 2
+    unsigned long long* __restrict__ bkeys = p.keys; uint32_t* __restrict__ bpixel = p.pixel; float* __restrict__ bz = p.zbuf; const float4* __restrict__ bxf = p.xf;
+#else
+    unsigned long long* bkeys = p.keys; uint32_t* bpixel = p.pixel; float* bz = p.zbuf; const float4* bxf = p.xf;
+#endif
+    for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
+    {
+        const int x = rx0 + strip * 8 + px;
+        if(x > rx1) continue;
+        uint32_t off = (uint32_t) x * (uint32_t) p.yres + (uint32_t) (ry0 + py);     /* inside the frame: the checksum's position salt */
+        unsigned long long next_key = ry0 + py <= ry1 ? bkeys[fbase + off] : CLEAR_KEY;
+        for(int y = ry0 + py; y <= ry1; y += CTA_ROWS, off += CTA_ROWS)
+        {
+            const uint32_t g = fbase + off;
+            const unsigned long long key = next_key;
+            if(y + CTA_ROWS <= ry1) next_key = bkeys[g + CTA_ROWS];         /* one iteration ahead of its use */
+            uint32_t colour; float z;
+            direct_shade<COMPACT>(p, bxf, vbase, vflags, twm1, thm1, key, x, y, colour, z);
+            st_b64<HINT>(bkeys + g, CLEAR_KEY, pol);                     /* the buffer is all "no winner" again for the next batch */
+            st_b32<HINT>(bpixel + g, colour, pol);
+            st_b32<HINT>(bz + g, __float_as_uint(z), pol);
+            if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
+        }
+    }
+#else
+    /* per-view bases live outside the pixel loop; inside it everything is a 32-bit offset from them */
     const size_t frame = (size_t) p.xres * p.yres;
     unsigned long long* __restrict__ vkeys = p.keys + (size_t) view * frame;
     uint32_t* __restrict__ vpixel = p.pixel + (size_t) view * frame;
     float* __restrict__ vz = p.zbuf + (size_t) view * frame;
     const float4* __restrict__ xf = p.xf + (size_t) view * p.nuniq;
-    uint32_t* vflags = p.flags + view;
-    const float twm1 = gel::i2f(p.tw - 1), thm1 = gel::i2f(p.th - 1);
-    const int nstrips = (rx1 - rx0 + 8) / 8;
     for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
         const int x = rx0 + strip * 8 + px;
@@ -705,13 +743,14 @@ direct_resolve_kernel(DirectParams p)
             const unsigned long long key = next_key;
             if(y + CTA_ROWS <= ry1) next_key = vkeys[off + CTA_ROWS];         /* one iteration ahead of its use */
             uint32_t colour; float z;
-            direct_shade<COMPACT>(p, xf, vflags, twm1, thm1, key, x, y, colour, z);
+            direct_shade<COMPACT>(p, xf, 0u, vflags, twm1, thm1, key, x, y, colour, z);
             st_b64<HINT>(vkeys + off, CLEAR_KEY, pol);                    /* the buffer is all "no winner" again for the next batch */
             st_b32<HINT>(vpixel + off, colour, pol);
             st_b32<HINT>(vz + off, __float_as_uint(z), pol);
             if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
         }
     }
+#endif
     if(HASH)
     {
         for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }

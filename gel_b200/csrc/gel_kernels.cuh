@@ -67,7 +67,13 @@ constexpr int FAR_CAP = 4096;       /* far triangles a CTA can park per tile (16
 constexpr int TWO_PHASE_MIN = GEL_TWO_PHASE_MIN;  /* tiles with fewer entries are rasterised in one phase                */
 constexpr int MAX_BATCH = 256;     /* views per launch set (the work list packs the view in 8 bits)         */
 constexpr int DEFER_MAX = GEL_DEFER_MAX;      /* large triangles per round left to the CTA-wide sweep (their setup records wait in shared memory) */
-constexpr int RESET_BOX_COLS = 4;  /* tile columns one TMA tensor store resets (box = 32 rows x 4 columns = 512 bytes of pattern)  */
+#ifndef GEL_RESET_BOX_COLS
+#define GEL_RESET_BOX_COLS 16
+#endif
+static_assert(GEL_TW % GEL_RESET_BOX_COLS == 0, "a tile is a whole number of reset boxes");
+constexpr int RESET_BOX_COLS = GEL_RESET_BOX_COLS;  /* tile columns one TMA tensor store resets (box = 32 rows x 16 columns = 2 KB of pattern): the copy unit takes its
+                                     * operands from uniform registers, so every store is issued by ONE lane at a time (ptxas loops over the active
+                                     * lanes, ~15 instructions per store) -- few large boxes, not many small ones */
 constexpr int CLEAR_CHUNK = 8;     /* tiles a CTA checks (and resets when untouched) per work item        */
 constexpr int SEG_SLOTS = RASTER_THREADS;   /* segments staged per round (one per thread)                 */
 constexpr int NCHAIN = 8;          /* parallel segment chains per tile (chunk % NCHAIN)                   */
@@ -444,8 +450,8 @@ struct WarpScratch
 
 struct RasterSmem
 {
-    alignas(128) uint32_t pat_pixel[TH * RESET_BOX_COLS];   /* 512 B of 0x00000000: source of the TMA stores that reset pixels */
-    alignas(128) uint32_t pat_z[TH * RESET_BOX_COLS];       /* 512 B of 0xFF7FFFFF (-FLT_MAX): the same for z                   */
+    alignas(128) uint32_t pat_pixel[TH * RESET_BOX_COLS];   /* 2 KB of 0x00000000: source of the TMA stores that reset pixels */
+    alignas(128) uint32_t pat_z[TH * RESET_BOX_COLS];       /* 2 KB of 0xFF7FFFFF (-FLT_MAX): the same for z                   */
     unsigned long long keys[TW * TH];   /* 8 KB  depth+winner per pixel, index key_slot(x_local, y_local) */
     WarpScratch ws[RASTER_WARPS];
     int seg_first[SEG_SLOTS];
@@ -570,33 +576,23 @@ __device__ __forceinline__ void resolve_swept(RasterSmem& sm, WarpScratch& ws, i
     if(key > *reinterpret_cast<volatile unsigned long long*>(k)) atomicMax(k, key);
 }
 
+/* tile g of the batch (view-major), when no triangle touches it: geometry for the reset */
+__device__ __forceinline__ bool untouched_tile(const RasterParams& p, int g, int& view, int& px0, int& py0, int& px1, int& py1)
+{
+    if(g >= p.ntiles * p.nviews || __ldg(p.tile_lit + g)) return false;
+    view = g / p.ntiles;
+    const int tile = g - view * p.ntiles;
+    const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
+    px0 = tx * TW; py0 = ty * TH;
+    px1 = min(px0 + TW, p.xres) - 1; py1 = min(py0 + TH, p.yres) - 1;
+    return true;
+}
+
 template<bool HASH>
 __device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int g, int lane, uint32_t pat_pixel, uint32_t pat_z)
 {
-    if(g >= p.ntiles * p.nviews || __ldg(p.tile_lit + g)) return;
-    const int view = g / p.ntiles, tile = g - view * p.ntiles;
-    const int tx = tile / p.tiles_y, ty = tile - tx * p.tiles_y;
-    const int px0 = tx * TW, py0 = ty * TH;
-    const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
-    if(!HASH && p.tma_reset)
-    {
-        /* TMA tensor stores (cp.async.bulk.tensor, SASS UTMASTG): lane k < 8 resets columns [4k, 4k + 4) of the pixel tile,
-         * lane 8 + k the same columns of the z tile -- one warp instruction issues the whole tile (16 boxes of 32 rows x 4
-         * columns, 8 KB) from two constant 512-byte patterns in shared memory; the copy unit generates the addresses and clips
-         * boxes at the frame's edges, so the reset costs the rasteriser CTAs 2 instructions per tile instead of ~250 */
-        constexpr int BOXES = TW / RESET_BOX_COLS;
-        const int col = px0 + (lane & (BOXES - 1)) * RESET_BOX_COLS;
-        if(lane < 2 * BOXES && col <= px1)
-        {
-            const bool zb = lane >= BOXES;
-            const unsigned long long tm = reinterpret_cast<unsigned long long>(zb ? &p.tm_z : &p.tm_pixel);
-            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                         :: "l"(tm), "r"(py0), "r"(col), "r"(view), "r"(zb ? pat_z : pat_pixel) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");     /* bounds the groups a thread has in flight */
-        }
-        return;
-    }
+    int view, px0, py0, px1, py1;
+    if(!untouched_tile(p, g, view, px0, py0, px1, py1)) return;
     uint32_t* pixel = p.pixel + (size_t) view * p.xres * p.yres;
     float* zbuf = p.zbuf + (size_t) view * p.xres * p.yres;
     if(!HASH && (p.yres & 3) == 0 && py1 - py0 + 1 == TH)
@@ -631,6 +627,41 @@ __device__ __forceinline__ void reset_untouched_tile(const RasterParams& p, int 
         for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
         if(lane == 0) { atomicAdd(p.hash + 2 * view, hp); atomicAdd(p.hash + 2 * view + 1, hz); }
     }
+}
+
+/* The `count` tiles first, first + step, ... : reset those no triangle touches.
+ * TMA form (cp.async.bulk.tensor, SASS UTMASTG): LANE j checks tile j -- flag load and the two divisions of the tile's position
+ * run once for all the tiles -- and issues the tile's 2 x (TW / RESET_BOX_COLS) tensor stores itself: boxes of 32 rows x 16 columns
+ * (pixels, then z) from two constant 2 KB patterns in shared memory; the copy unit generates the addresses and clips boxes at the
+ * frame's edges.  A tensor store takes its operands from uniform registers, so ptxas serialises the lanes that issue one (~15
+ * instructions per store): 4 stores per tile cost the rasteriser ~60 instructions.  (Round 2 used 16 boxes of 4 columns issued by 16
+ * lanes "in one instruction": the capture showed 240 instructions per tile, 5 % of the kernel.)
+ * Otherwise (checksums wanted, no tensor map): the warp-wide store loops, tile after tile. */
+template<bool HASH>
+__device__ __forceinline__ void reset_untouched_tiles(const RasterParams& p, int first, int step, int count, int lane, uint32_t pat_pixel, uint32_t pat_z)
+{
+    if(!HASH && p.tma_reset)
+    {
+        int view, px0, py0, px1, py1;
+        if(lane < count && untouched_tile(p, first + lane * step, view, px0, py0, px1, py1))
+        {
+            const unsigned long long tmp = reinterpret_cast<unsigned long long>(&p.tm_pixel), tmz = reinterpret_cast<unsigned long long>(&p.tm_z);
+            #pragma unroll
+            for(int b = 0; b < TW / RESET_BOX_COLS; b++)
+            {
+                const int col = px0 + b * RESET_BOX_COLS;
+                if(col > px1) break;
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             :: "l"(tmp), "r"(py0), "r"(col), "r"(view), "r"(pat_pixel) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             :: "l"(tmz), "r"(py0), "r"(col), "r"(view), "r"(pat_z) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");     /* bounds the groups a thread has in flight */
+        }
+        return;
+    }
+    for(int j = 0; j < count; j++) reset_untouched_tile<HASH>(p, first + j * step, lane, pat_pixel, pat_z);
 }
 
 template<bool HASH>
@@ -678,7 +709,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
         const int view = sm.it_view;
         if(view < 0) break;
         if(tid == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, CLEAR_CHUNK); }
-        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, sm.it_clear + j, lane, pat_pixel, pat_z);
+        reset_untouched_tiles<HASH>(p, sm.it_clear + warp, RASTER_WARPS, (CLEAR_CHUNK - warp + RASTER_WARPS - 1) / RASTER_WARPS, lane, pat_pixel, pat_z);
         const int tile = sm.it_tile;
         const int px0 = sm.it_tx * TW, py0 = sm.it_ty * TH;
         const int px1 = min(px0 + TW, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
@@ -1048,7 +1079,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
     /* no lit tile left: finish the chunk already reserved, then drain the reset queue */
     for(int base = sm.it_clear; base < nclear; )
     {
-        for(int j = warp; j < CLEAR_CHUNK; j += RASTER_WARPS) reset_untouched_tile<HASH>(p, base + j, lane, pat_pixel, pat_z);
+        reset_untouched_tiles<HASH>(p, base + warp, RASTER_WARPS, (CLEAR_CHUNK - warp + RASTER_WARPS - 1) / RASTER_WARPS, lane, pat_pixel, pat_z);
         __syncthreads();
         if(tid == 0) sm.it_clear = atomicAdd(p.work_counter + 1, CLEAR_CHUNK);
         __syncthreads();

@@ -115,6 +115,10 @@ cudaError_t sync_ctx(gelcu_ctx* c)
     return first;
 }
 
+/* the rasterisers are compiled for GEL_RASTER_MINB resident CTAs per SM: their shared memory has to allow as many (228 KB per SM, 1 KB reserved per CTA) */
+static_assert((sizeof(BandSmem) + 1024) * GEL_RASTER_MINB <= 233472, "raster_band_kernel: shared memory leaves fewer resident CTAs than the launch bounds assume");
+/* (raster_kernel, the CTA-per-tile form kept as raster_mode 0, runs 7 CTAs per SM since the reset patterns grew to 2 x 2 KB: gelcu_create asks the occupancy API) */
+
 #ifndef GEL_RESOLVE_CTAS
 #define GEL_RESOLVE_CTAS 1024
 #endif
@@ -207,9 +211,13 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
 
 int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 {
-    if(c->batch_opt > 0) return std::min(c->batch_opt, MAX_BATCH);
+    /* the direct pipeline's resolve pass addresses the batch's frames and transformed vertices with 32-bit element indices */
+    size_t most = MAX_BATCH;
+    if(active_pipeline(c) == 2)
+        most = std::max<size_t>(1, std::min<size_t>(most, 0xFFFFFFFFull / std::max<size_t>(1, std::max((size_t) c->xres * c->yres, (size_t) c->nuniq))));
+    if(c->batch_opt > 0) return (int) std::min<size_t>((size_t) c->batch_opt, most);
     const size_t budget = (size_t) 24 << 30;
-    return (int) std::min<size_t>(MAX_BATCH, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));
+    return (int) std::min<size_t>(most, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));
 }
 
 /* Enqueues the kernels for `n` views starting at d_views + first into frame buffer `buf`. */
