@@ -26,6 +26,9 @@
 
 namespace gelk {
 
+#ifndef GEL_BAND_ROW_TRIM
+#define GEL_BAND_ROW_TRIM 1                       /* per-column exact row trimming in the unit prologue (0 = walk the bbox rows) */
+#endif
 constexpr int BAND_W = 8;                         /* pixel columns of a band */
 constexpr int BANDS = TW / BAND_W;                /* bands per tile */
 constexpr int BAND_UNITS = 32 * BAND_W;           /* most column units a batch of 32 triangles has inside a band */
@@ -38,11 +41,11 @@ struct BandScratch
 {
     unsigned long long keys[BAND_W * TH];         /* 2 KB  depth + winner per pixel: band_slot(x_local, y_local)                 */
     float4 slab[4][32];                           /* 2 KB  per-triangle constants of the current 32 entries                     */
-    unsigned short unit[BAND_UNITS];              /* 512 B column unit -> (lane << 5 | x_local)                                 */
+    unsigned char unit[BAND_UNITS];               /* 256 B column unit -> (lane << 3 | x_local)                                 */
     float2 q_n[QCAP];                             /* survivors of the cheap tests, waiting for the division stage: (nv, nw)     */
     uint32_t q_id[QCAP];                          /*                          triangle slot << 10 | x_local << 5 | y_local      */
     uint32_t bbox[32];                            /* band-local bbox: x0 | x1 << 5 | y0 << 10 | y1 << 15 | guard << 20          */
-    float den_hi[32];
+    float2 etrim[32];                             /* slack terms of the row trimming (K2 record, quad 7: ev, ew)               */
     int seg_first[BAND_SEGS], seg_pre[BAND_SEGS]; /* staged segments: first entry, exclusive prefix of the sizes                */
     uint32_t hiz[4];                              /* per 8x8 block of the band: min depth key after the near phase             */
 };
@@ -56,6 +59,16 @@ struct BandSmem
 
 /* column x owns 32 slots; its rows are rotated by 2x so that one row of the band's 8 columns lands on 8 different bank pairs */
 __device__ __forceinline__ int band_slot(int xl, int yl) { return xl * TH + ((yl + 2 * xl) & 31); }
+
+/* Queue ticket for ONE lane.  Spelled as PTX: atomicAdd() under `if(lane == 0)` is turned by the compiler into its warp-aggregated
+ * form (vote, leader atomic, SHFL of the result), and that shuffle waits for the atomic's round trip on the spot -- the capture showed
+ * 13 % of the kernel's stall samples there.  This way the ticket is only waited for where it is used: at the top of the NEXT item. */
+__device__ __forceinline__ int queue_ticket(int* counter, int n)
+{
+    int old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(n) : "memory");
+    return old;
+}
 
 template<bool HASH>
 __global__ void __launch_bounds__(RASTER_THREADS, GEL_RASTER_MINB)
@@ -79,7 +92,7 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
 
     /* lane 0 owns the warp's queue cursors: the atomics for the NEXT item are issued when the current one starts */
     int g_next = 0, c_next = 0;
-    if(lane == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, BAND_CLEAR); }
+    if(lane == 0) { g_next = queue_ticket(p.work_counter, 1); c_next = queue_ticket(p.work_counter + 1, BAND_CLEAR); }
 
     for(;;)
     {
@@ -90,12 +103,12 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
             for(int base = c0; base < nclear; )
             {
                 reset_untouched_tiles<HASH>(p, base, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
-                if(lane == 0) base = atomicAdd(p.work_counter + 1, BAND_CLEAR);
+                if(lane == 0) base = queue_ticket(p.work_counter + 1, BAND_CLEAR);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
             }
             break;
         }
-        if(lane == 0) { g_next = atomicAdd(p.work_counter, 1); c_next = atomicAdd(p.work_counter + 1, BAND_CLEAR); }
+        if(lane == 0) { g_next = queue_ticket(p.work_counter, 1); c_next = queue_ticket(p.work_counter + 1, BAND_CLEAR); }
         reset_untouched_tiles<HASH>(p, c0, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
 
         const uint32_t item = __ldg(p.lit_list + g / BANDS);
@@ -104,8 +117,8 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
         const int px0 = tx * TW + band * BAND_W, py0 = ty * TH;
         const int px1 = min(px0 + BAND_W, p.xres) - 1, py1 = min(py0 + TH, p.yres) - 1;
         if(px0 > px1) continue;                                           /* the band lies right of the frame */
-        uint32_t* __restrict__ pixel = p.pixel + (size_t) view * frame;
-        float* __restrict__ zbuf = p.zbuf + (size_t) view * frame;
+        /* element index of the band's first pixel in the batch's frame buffers (32 bits: the host keeps views per batch x frame < 2^32) */
+        const uint32_t gband = (uint32_t) view * (uint32_t) frame + (uint32_t) px0 * (uint32_t) p.yres + (uint32_t) (py0 + lane);
         const float4* __restrict__ vrec = p.vrec + (size_t) view * p.ntri * VREC_QUADS;
         const uint4* __restrict__ descs = p.descs + (size_t) view * p.cap_d;
         const uint32_t* __restrict__ entries = p.entries + (size_t) view * p.cap_e;
@@ -160,30 +173,49 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
                     nun = (int) ((r.bbox >> 5) & 31) - x + 1;             /* one unit per bbox column inside the band: <= 8 */
                     ws.slab[0][lane] = r.q0; ws.slab[1][lane] = r.q1; ws.slab[2][lane] = r.q2; ws.slab[3][lane] = r.q3;
                     ws.bbox[lane] = r.bbox;
-                    ws.den_hi[lane] = r.q2.w * U_SLACK;
+                    const float4 r7 = __ldg(vrec + (size_t) tri * VREC_QUADS + 7);
+                    ws.etrim[lane] = make_float2(r7.z, r7.w);
                 }
             }
             int uincl = nun;
             for(int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xFFFFFFFFu, uincl, d); if(lane >= d) uincl += n; }
             const int ustart = uincl - nun;
             const int utotal = __shfl_sync(0xFFFFFFFFu, uincl, 31);       /* <= BAND_UNITS */
-            for(int k = 0; k < nun; k++) ws.unit[ustart + k] = (unsigned short) (lane << 5 | (x + k));
+            for(int k = 0; k < nun; k++) ws.unit[ustart + k] = (unsigned char) (lane << 3 | (x + k));
             __syncwarp();
             for(int u0 = 0; u0 < utotal; u0 += 32)
             {
                 /* stage 1: numerators of v and w (main.c:325-328) down the column; exact cheap rejections */
                 const bool act = u0 + lane < utotal;
                 const uint32_t o = act ? ws.unit[u0 + lane] : 0u;
-                const int src = o >> 5, xl = o & 31;
+                const int src = o >> 3, xl = o & 7;
                 const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src];
                 const uint32_t bb = ws.bbox[src];
-                const float den_hi = ws.den_hi[src];
-                const int y0l = (bb >> 10) & 31;
-                const int rows = act ? (int) ((bb >> 15) & 31) - y0l + 1 : 0;
-                const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
+                const float den_hi = q2.w * U_SLACK;
+                int y0l = (bb >> 10) & 31;
+                int rows = act ? (int) ((bb >> 15) & 31) - y0l + 1 : 0;
                 const float eps = (bb >> 20) & 1 ? -GUARD_EPS : -INFINITY;
                 const float v2x = gel::sub(gel::i2f(px0 + xl), q0.x);
                 const float cx0 = gel::mul(v2x, q0.z), cx1 = gel::mul(v2x, q1.x);
+#if GEL_BAND_ROW_TRIM
+                {
+                    /* Row trimming (gel_math.h: row_trim): the numerators at the column's first and last row -- the row loop's own
+                     * operations -- say how many rows at either end cannot pass the cheap tests; a triangle much larger than a band
+                     * covers a chord of each bbox column, and the loop below then walks the chord instead of the bbox. */
+                    const float2 et = ws.etrim[src];
+                    const int n = max(rows - 1, 0);
+                    const float ya = gel::sub(gel::i2f(py0 + y0l), q0.y), yb = gel::sub(gel::i2f(py0 + y0l + n), q0.y);
+                    const float a20 = gel::add(gel::add(cx0, gel::mul(ya, q0.w)), q1.z), a21 = gel::add(gel::add(cx1, gel::mul(ya, q1.y)), q1.w);
+                    const float b20 = gel::add(gel::add(cx0, gel::mul(yb, q0.w)), q1.z), b21 = gel::add(gel::add(cx1, gel::mul(yb, q1.y)), q1.w);
+                    const float nv0 = gel::sub(gel::mul(q2.z, a20), gel::mul(q2.y, a21)), nw0 = gel::sub(gel::mul(q2.x, a21), gel::mul(q2.y, a20));
+                    const float nv1 = gel::sub(gel::mul(q2.z, b20), gel::mul(q2.y, b21)), nw1 = gel::sub(gel::mul(q2.x, b21), gel::mul(q2.y, b20));
+                    int lo, hi;
+                    gel::row_trim(nv0, nw0, nv1, nw1, eps, den_hi, et.x, et.y, n, lo, hi);
+                    y0l += lo;
+                    rows = max(rows - lo - hi, 0);
+                }
+#endif
+                const int maxrows = __reduce_max_sync(0xFFFFFFFFu, rows);
                 float fy = gel::i2f(py0 + y0l);
                 uint32_t id = (uint32_t) src << 10 | (uint32_t) xl << 5 | (uint32_t) y0l;
                 for(int r = 0; r < maxrows; r++, id++)
@@ -370,12 +402,12 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
                     atomicOr(p.flags + view, FLAG_TEXCLAMP);   /* the reference reads out of bounds here (R) */
                     xx = min(max(xx, 0), p.tw - 1); yy = min(max(yy, 0), p.th - 1);
                 }
-                colour = gel::pshade(__ldg(p.tex + xx + yy * p.tw), shading);
+                colour = gel::pshade(__ldg(p.tex + (uint32_t) (xx + yy * p.tw)), shading);
             }
-            const int idx = y + x * p.yres;
-            pixel[idx] = colour;
-            zbuf[idx] = z;
-            if(HASH) { hp += gel::salt_mix(colour, (uint32_t) idx); hz += gel::salt_mix(__float_as_uint(z), (uint32_t) idx); }
+            const uint32_t gi = gband + (uint32_t) xl * (uint32_t) p.yres;
+            p.pixel[gi] = colour;
+            p.zbuf[gi] = z;
+            if(HASH) { const uint32_t idx = (uint32_t) (y + x * p.yres); hp += gel::salt_mix(colour, idx); hz += gel::salt_mix(__float_as_uint(z), idx); }
         }
         if(HASH)
         {

@@ -87,9 +87,7 @@ struct DirectParams
 
 struct DirectScratch               /* per warp */
 {
-    float4 slab[3][32];                  /* q0, q1, q2 of the current 32 triangles (gel_kernels.cuh, slab layout) */
-    float4 q3[32];                       /* az, bz, cz, ~tri */
-    float den[32];                       /* q2.w once more: with q3 all the division stage needs of a triangle (one 4-byte and one 16-byte read per survivor) */
+    float4 slab[4][32];                  /* q0 .. q3 of the current 32 triangles (gel_kernels.cuh, slab layout) */
     uint32_t unit[DIRECT_UNIT_WINDOW];   /* lane << 13 | x */
     uint32_t cand[DIRECT_CAND];          /* triangle ids */
     float2 q_n[QCAP];
@@ -204,7 +202,7 @@ __device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned l
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
     const uint32_t src = id >> 26, x = (id >> 13) & 8191u, y = id & 8191u;
-    const unsigned long long key = fragment_key(n.x, n.y, ws.den[src], ws.q3[src]);
+    const unsigned long long key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
     if(key) key_max<HINT>(keys + (x * (uint32_t) p.yres + y), key, pol);  /* 32-bit unsigned offset inside the view's frame */
 }
 
@@ -347,8 +345,7 @@ direct_raster_kernel(DirectParams p)
                     ws.slab[0][lane] = make_float4(s.ax, s.ay, s.v0x, s.v0y);
                     ws.slab[1][lane] = make_float4(s.v1x, s.v1y, s.k0, s.k1);
                     ws.slab[2][lane] = q2;
-                    ws.q3[lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
-                    ws.den[lane] = q2.w;
+                    ws.slab[3][lane] = make_float4(s.az, s.bz, s.cz, __uint_as_float(0xFFFFFFFFu - tri));
                     ws.bx[lane] = (uint32_t) x0 | (uint32_t) x1 << 16;
                     ws.by[lane] = (uint32_t) y0 | (uint32_t) y1 << 13 | (guard ? 1u << 26 : 0u);
                     ws.den_hi[lane] = s.den * sg * U_SLACK;
@@ -430,7 +427,7 @@ direct_raster_kernel(DirectParams p)
         {
             const int src = __ffs(sm) - 1;
             sm &= sm - 1;
-            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src], q3 = ws.q3[src];
+            const float4 q0 = ws.slab[0][src], q1 = ws.slab[1][src], q2 = ws.slab[2][src], q3 = ws.slab[3][src];
             const uint32_t xx = ws.bx[src], yy = ws.by[src];
             const int x0 = xx & 0xFFFF, x1 = xx >> 16, y0 = yy & 8191, y1 = (yy >> 13) & 8191;
             const float eps = (yy >> 26) & 1 ? -GUARD_EPS : -INFINITY;

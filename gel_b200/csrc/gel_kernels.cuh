@@ -280,7 +280,10 @@ bin_kernel(BinParams p)
                                    fmaxf(a.z, fmaxf(b.z, c.z)));
                 r[5] = make_float4(a.w, b.w, c.w, 0.0f);
                 r[6] = make_float4(ta.x, ta.y, tb.x, tb.y);
-                r[7] = make_float4(tc.x, tc.y, 0.0f, 0.0f);
+                /* slack terms of the band rasteriser's row trimming (gel_math.h: row_trim) over the whole clipped bbox */
+                float ev = INFINITY, ew = INFINITY;
+                if(drawable) gel::trim_slack(s.ax, s.ay, s.v0x, s.v0y, s.v1x, s.v1y, s.k0, s.k1, s.d00 * sg, s.d01 * sg, s.d11 * sg, s.den * sg, x0, y0, x1, y1, ev, ew);
+                r[7] = make_float4(tc.x, tc.y, ev, ew);
             }
             if(x0 <= x1 && y0 <= y1)
             {

@@ -229,6 +229,84 @@ GEL_HD void bbox_trim(float ax, float ay, float v0x, float v0y, float v1x, float
     x0 += left ? 1 : 0; x1 -= right ? 1 : 0; y0 += bottom ? 1 : 0; y1 -= top ? 1 : 0;
 }
 
+/* Row trimming of one bbox COLUMN (tile pipeline, band rasteriser).
+ *
+ * A large triangle covers a chord of each of its bbox columns; the rows above and below the chord fail the reference's inside test
+ * and the kernel only finds that out by testing them.  row_trim removes, from the two ends of a column's row range, rows that
+ * provably fail the kernels' exact cheap rejection (and hence main.c:352) -- the same three conditions as bbox_trim:
+ *     nv < eps (eps = -1e-20, den <= 1e18)        nw < eps        nv + nw > den_hi = den (1 + 1e-5)
+ *
+ * Setting.  Column x, rows y_0 .. y_0 + n (n >= 1).  For one condition let a(j) be the float value the row loop computes at row
+ * y_0 + j (nv, nw, or -(nv + nw)), a0 = a(0), a1 = a(n) the two END values, evaluated with the row loop's own operations;
+ * "rejected" means a(j) < t0 (t0 = eps, eps, -den_hi).  In real arithmetic on the same float constants the quantity is AFFINE in
+ * j:  A(j) = A0 + (j / n)(A1 - A0), and |a(j) - A(j)| <= Et for every pixel of the triangle's bbox, Et <= 8u M (forward error
+ * analysis as in bbox_trim; M = the magnitude |A| M20 + |C| M21 (+ the w analogue for the sum) + den).  trim_slack supplies
+ * e = 64u M + 1e-24 >= 8 Et, and t = fl(t0 - e).
+ *
+ * Claim.  With g0 = fl(t - a0) > 0 and dl = fl(fl(a1 - a0) + e):  every integer row j in [0, n] with
+ *         j < n g0 / dl   (dl > 0)        or any j at all   (dl <= 0)
+ * has a(j) < t0.  Proof: A(j) <= a0 + Et + (j/n)(a1 - a0 + 2Et), so a(j) <= a0 + (j/n) Cf + 2Et with Cf = a1 - a0 + 2Et.  Rounding
+ * of g0 and dl costs at most u(|t| + |a0|) + 2u|a1 - a0| + u e <= e/16 (|a| <= M(1 + 8u), u M <= e/64), hence g0 <= t0 - a0 - 2Et - e/2
+ * and dl >= Cf + e/2.  If Cf <= 0 then a(j) <= a0 + 2Et < t0.  If Cf > 0 then dl > Cf > 0 and j < n g0 / dl <= n (t0 - a0 - 2Et) / Cf
+ * gives (j/n) Cf < t0 - a0 - 2Et, i.e. a(j) < t0.  The quotient is evaluated approximately (MUFU reciprocal, ~1 ulp, three roundings) and multiplied by
+ * 0.999 before truncation, so the integer never exceeds the real bound; dl in (0, 1e-30] trims nothing (no reciprocal of a
+ * denormal); a NaN anywhere makes every comparison false: nothing is trimmed.  If BOTH ends are below t the whole column goes
+ * (A is affine: A(j) <= max(A0, A1)) -- bbox_trim's argument.  By symmetry the same holds from the other end with a0, a1 swapped.
+ * Cuts of different conditions combine: rows j < max over the conditions of their lower cuts are each rejected by the condition
+ * that attains the maximum; likewise at the top.  Soundness is also brute-forced on the host (tests/test_emu_math.py). */
+/* approximate reciprocal for the trimming quotient (never part of the reference's arithmetic); the argument is > 1e-30 where it counts */
+#if defined(__CUDA_ARCH__)
+GEL_HD float fast_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+#else
+GEL_HD float fast_rcp(float a) { return 1.0f / a; }
+#endif
+
+/* e_v, e_w of the proof for one triangle, from its (frame-clipped) bbox; +inf when the error analysis does not apply (overflow-
+ * sized terms, NaN): every trimming comparison is then false.  Same magnitudes as bbox_trim, den added. */
+GEL_HD void trim_slack(float ax, float ay, float v0x, float v0y, float v1x, float v1y, float k0, float k1,
+                       float B /* d00 */, float C /* d01 */, float A /* d11 */, float D /* den, > 0 */,
+                       int x0, int y0, int x1, int y1, float& ev, float& ew)
+{
+    const float xa = sub(i2f(x0), ax), xb = sub(i2f(x1), ax), ya = sub(i2f(y0), ay), yb = sub(i2f(y1), ay);
+    const float mx = fmaxf(fabsf(xa), fabsf(xb)), my = fmaxf(fabsf(ya), fabsf(yb));
+    const float m20 = add(add(mul(mx, fabsf(v0x)), mul(my, fabsf(v0y))), fabsf(k0));
+    const float m21 = add(add(mul(mx, fabsf(v1x)), mul(my, fabsf(v1y))), fabsf(k1));
+    const float tv_mag = add(add(mul(fabsf(A), m20), mul(fabsf(C), m21)), D), tw_mag = add(add(mul(fabsf(B), m21), mul(fabsf(C), m20)), D);
+    const bool ok = add(tv_mag, tw_mag) <= 1e30f && add(add(fabsf(A), fabsf(B)), fabsf(C)) <= 1e12f && D > 0.0f;
+    const float u64 = 3.814697265625e-06f;                               /* 64 u */
+    ev = ok ? add(mul(u64, tv_mag), 1e-24f) : INFINITY;
+    ew = ok ? add(mul(u64, tw_mag), 1e-24f) : INFINITY;
+}
+
+/* one condition: end values a0 (row 0) and a1 (row n), threshold t = t0 - e, nf = (float) n; raises lo / hi to the rows that can go
+ * at either end.  Straight-line (selects only): it runs in the rasteriser's unit prologue with all 32 lanes on different columns. */
+GEL_HD void row_trim_cond(float a0, float a1, float t, float e, int n, float nf, int& lo, int& hi)
+{
+    const float g0 = sub(t, a0), g1 = sub(t, a1);
+    const bool f0 = g0 > 0.0f, f1 = g1 > 0.0f;                            /* rejected at the first / last row (NaN: false) */
+    const float g = f0 ? g0 : g1;
+    const float d = sub(a1, a0);
+    const float dl = add(f0 ? d : -d, e);
+    int c = trunc_i(mul(mul(mul(nf, g), fast_rcp(dl)), 0.999f));          /* NaN -> 0, huge -> INT_MAX */
+    c = c < 0 ? 0 : c > n + 1 ? n + 1 : c;
+    c = dl > 1e-30f ? c : dl <= 0.0f ? n + 1 : 0;                         /* no reciprocal of a denormal; NaN: leave the column alone */
+    c = (f0 && f1) ? n + 1 : c;                                           /* both ends rejected: the whole column */
+    c = (f0 || f1) ? c : 0;
+    const int cl = f0 ? c : 0, ch = f0 ? 0 : c;
+    lo = cl > lo ? cl : lo; hi = ch > hi ? ch : hi;
+}
+
+/* Rows [0, n] of a column -> skip `lo` rows at the bottom and `hi` at the top (lo + hi may exceed n + 1: the column is empty).
+ * (nv0, nw0) / (nv1, nw1): the numerators at the first / last row, den_hi = den (1 + 1e-5), eps = -1e-20 or -inf (no guard). */
+GEL_HD void row_trim(float nv0, float nw0, float nv1, float nw1, float eps, float den_hi, float ev, float ew, int n, int& lo, int& hi)
+{
+    lo = 0; hi = 0;
+    const float es = add(ev, ew), nf = i2f(n);
+    row_trim_cond(nv0, nv1, sub(eps, ev), ev, n, nf, lo, hi);
+    row_trim_cond(nw0, nw1, sub(eps, ew), ew, n, nf, lo, hi);
+    row_trim_cond(-add(nv0, nw0), -add(nv1, nw1), -add(den_hi, es), es, n, nf, lo, hi);
+}
+
 /* Orderable 32-bit key of a float: a > b  <=>  zkey(a) > zkey(b) for all non-NaN a != b (and +0 > -0). */
 GEL_HD uint32_t zkey(float z)
 {

@@ -211,10 +211,9 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
 
 int default_batch(const gelcu_ctx* c, int cap_e, int cap_d)
 {
-    /* the direct pipeline's resolve pass addresses the batch's frames and transformed vertices with 32-bit element indices */
-    size_t most = MAX_BATCH;
-    if(active_pipeline(c) == 2)
-        most = std::max<size_t>(1, std::min<size_t>(most, 0xFFFFFFFFull / std::max<size_t>(1, std::max((size_t) c->xres * c->yres, (size_t) c->nuniq))));
+    /* the shade passes address the batch's frames (and the direct pipeline its transformed vertices) with 32-bit element indices */
+    size_t most = std::max<size_t>(1, std::min<size_t>(MAX_BATCH, 0xFFFFFFFFull / std::max<size_t>(1, (size_t) c->xres * c->yres)));
+    if(active_pipeline(c) == 2) most = std::max<size_t>(1, std::min<size_t>(most, 0xFFFFFFFFull / std::max<size_t>(1, (size_t) c->nuniq)));
     if(c->batch_opt > 0) return (int) std::min<size_t>((size_t) c->batch_opt, most);
     const size_t budget = (size_t) 24 << 30;
     return (int) std::min<size_t>(most, std::max<size_t>(1, budget / per_view_bytes(c, cap_e, cap_d)));

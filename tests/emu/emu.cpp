@@ -115,3 +115,58 @@ extern "C" uint64_t emu_trim_soundness(const float* vew, int ntri, int xres, int
     }
     return wrong;
 }
+
+/* Brute-force soundness of row_trim (gel_math.h), the band rasteriser's per-column row trimming: every triangle's clipped bbox is
+ * cut into the rasteriser's 32-row tile segments; for every column of every segment the two end rows are evaluated with the row
+ * loop's operations, row_trim says how many rows go at either end, and every row it removes is evaluated the reference's way
+ * (tbarycenter + the >= 0 test, main.c:316-332, 352) and the kernels' way (the exact cheap rejection) -- none may be inside, all
+ * must be rejected.  Returns the violations; counts[0] += rows tested without trimming, counts[1] += rows left, counts[2] += inside. */
+extern "C" uint64_t emu_row_trim_soundness(const float* vew, int ntri, int xres, int yres, uint64_t* counts)
+{
+    uint64_t wrong = 0;
+    for(int t = 0; t < ntri; t++)
+    {
+        const float* p = vew + 9 * (size_t) t;
+        const gel::TriSetup s = gel::tri_setup(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+        const int x0 = s.x0 < 0 ? 0 : s.x0, y0 = s.y0 < 0 ? 0 : s.y0, x1 = s.x1 > xres - 1 ? xres - 1 : s.x1, y1 = s.y1 > yres - 1 ? yres - 1 : s.y1;
+        const float ad = fabsf(s.den);
+        if(x0 > x1 || y0 > y1 || !(ad > 0.0f)) continue;
+        const float sg = s.den < 0.0f ? -1.0f : 1.0f;
+        const float B = s.d00 * sg, C = s.d01 * sg, A = s.d11 * sg, D = s.den * sg;
+        const float eps = ad <= 1e18f ? -1e-20f : -INFINITY, den_hi = gel::mul(D, 1.00001f);
+        float ev, ew;
+        gel::trim_slack(s.ax, s.ay, s.v0x, s.v0y, s.v1x, s.v1y, s.k0, s.k1, B, C, A, D, x0, y0, x1, y1, ev, ew);
+        auto numer = [&](int x, int y, float& nv, float& nw)
+        {
+            const float v2x = gel::sub(gel::i2f(x), s.ax), cx0 = gel::mul(v2x, s.v0x), cx1 = gel::mul(v2x, s.v1x);
+            const float v2y = gel::sub(gel::i2f(y), s.ay);
+            const float d20 = gel::add(gel::add(cx0, gel::mul(v2y, s.v0y)), s.k0), d21 = gel::add(gel::add(cx1, gel::mul(v2y, s.v1y)), s.k1);
+            nv = gel::sub(gel::mul(A, d20), gel::mul(C, d21)); nw = gel::sub(gel::mul(B, d21), gel::mul(C, d20));
+        };
+        for(int ty = y0 / 32; ty <= y1 / 32; ty++)
+        {
+            const int ya = y0 > ty * 32 ? y0 : ty * 32, yb = y1 < ty * 32 + 31 ? y1 : ty * 32 + 31, n = yb - ya;
+            for(int x = x0; x <= x1; x++)
+            {
+                float nv0, nw0, nv1, nw1;
+                numer(x, ya, nv0, nw0); numer(x, yb, nv1, nw1);
+                int lo, hi;
+                gel::row_trim(nv0, nw0, nv1, nw1, eps, den_hi, ev, ew, n, lo, hi);
+                counts[0] += (uint64_t) (n + 1);
+                if(lo + hi < n + 1) counts[1] += (uint64_t) (n + 1 - lo - hi);
+                for(int y = ya; y <= yb; y++)
+                {
+                    float nv, nw, v, w, u, z, rv, rw;
+                    gel::bary_numerators(s, gel::i2f(x), gel::i2f(y), rv, rw);
+                    const bool inside = gel::bary_inside(s, rv, rw, v, w, u, z);
+                    counts[2] += inside;
+                    if(y - ya >= lo && yb - y >= hi) continue;               /* kept */
+                    numer(x, y, nv, nw);
+                    const bool rejected = nv < eps || nw < eps || gel::add(nv, nw) > den_hi;
+                    if(inside || !rejected) wrong++;
+                }
+            }
+        }
+    }
+    return wrong;
+}

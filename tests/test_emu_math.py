@@ -125,3 +125,40 @@ def test_bbox_trim_on_the_cfg3_sphere(emu):
         counts = (ctypes.c_uint64 * 3)(0, 0, 0)
         assert emu.emu_trim_soundness(vew.ctypes.data_as(_fp), vew.shape[0], 1100, 620, rounds, counts) == 0
         assert counts[1] < most * counts[0]
+
+
+@pytest.mark.parametrize("res", [(8192, 8192), (640, 480)])
+def test_row_trim_never_removes_a_row_that_could_pass(emu, res):
+    """Brute force for the band rasteriser's per-column row trimming (gel_math.h: row_trim): every row it removes from a column of a
+    triangle's bbox is evaluated the reference's way and the kernels' way -- none is inside, all are rejected by the exact cheap
+    tests.  Adversarial triangles (vertices on integer coordinates, slivers, steep z, 0.05 .. 40 px) plus large ones (the tile
+    pipeline's customers), and the trimming must remove a large share of the rows."""
+    emu.emu_row_trim_soundness.restype = ctypes.c_uint64
+    rng = np.random.default_rng(res[1])
+    small = _adversarial_triangles(rng, 600_000, res)
+    big = _adversarial_triangles(rng, 40_000, res)
+    c = big.reshape(-1, 3, 3)[:, :, :2].mean(1, keepdims=True)
+    big.reshape(-1, 3, 3)[:, :, :2] = np.clip(c + (big.reshape(-1, 3, 3)[:, :, :2] - c) * rng.uniform(1.0, 8.0, (big.shape[0], 1, 1)), 0.0, np.array([res[0] - 1.001, res[1] - 1.001]))
+    for tri, least in ((small, 0.95), (big.astype(np.float32), 0.75)):
+        counts = (ctypes.c_uint64 * 3)(0, 0, 0)
+        wrong = emu.emu_row_trim_soundness(np.ascontiguousarray(tri).ctypes.data_as(_fp), tri.shape[0], res[0], res[1], counts)
+        assert wrong == 0, f"{wrong} rows that pass were trimmed away"
+        assert counts[2] > 100_000 and counts[1] < least * counts[0], (counts[0], counts[1], counts[2])
+        assert counts[1] >= counts[2]                                           # every inside pixel is on a kept row
+
+
+def test_row_trim_on_the_cfg5_sphere(emu):
+    """The workload it is meant for: views of the 5 000-triangle sphere at 1080p -- no row that passes is removed, and the rows left are
+    close to the pixels inside (the figure quoted in DESIGN.md)."""
+    from gel_b200 import synth
+    import gel_b200, tempfile
+    emu.emu_row_trim_soundness.restype = ctypes.c_uint64
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "s.obj")
+        open(obj, "w").write(synth.sphere_obj_text(50, 50))
+        tv, tn, _ = gel_b200.load_obj(obj)
+    for xt in (0.0, 0.0767, 1.3, 3.9):
+        vew, _ = oracle.transform(tv, tn, oracle.view_basis(xt, 0.0), 1920, 1080)
+        counts = (ctypes.c_uint64 * 3)(0, 0, 0)
+        assert emu.emu_row_trim_soundness(vew.ctypes.data_as(_fp), vew.shape[0], 1920, 1080, counts) == 0
+        assert counts[2] <= counts[1] < 0.65 * counts[0]
