@@ -55,7 +55,7 @@ WORKLOADS = {
     "cfg5": ("sphere", 50, 256, 1920, 1080, 8192, "5 000-tri sphere, 8192 rotated views @ 1920x1080 sharded over the GPUs"),
 }
 SWEEP = {"cfg1": 64, "cfg2": 360, "cfg3": 64, "cfg5": 8192}          # views of the workload's full rotation, xt_k = 2 pi k / n
-KERNEL_SOURCES = ["gel_math.h", "gel_kernels.cuh", "gel_direct.cuh", "gel_sink.cuh", "gel_mesh.cuh", "gelcu.cu"]
+KERNEL_SOURCES = ["gel_math.h", "gel_kernels.cuh", "gel_band.cuh", "gel_direct.cuh", "gel_sink.cuh", "gel_mesh.cuh", "gelcu.cu"]
 
 
 def workload_config(name: str, ntri: int):
@@ -477,7 +477,8 @@ def bench_workload(name, world, rank, local_rank, workdir, steps, warmup, flush,
     fps = total_views / (worst_ms * 1e-3)
     dom_ms = max_over_ranks(stage["ms_dominant"])
     pipeline = {1: "tile", 2: "direct"}.get(int(st.get("pipeline", 1)), "tile")
-    dominant = "direct_raster_kernel<0>" if pipeline == "direct" else "raster_kernel"
+    band = not any(o.replace(" ", "") == "raster_mode=0" for o in (opts or []))
+    dominant = "direct_raster_kernel<0>" if pipeline == "direct" else "raster_band_kernel" if band else "raster_kernel"
 
     peak, peak_src = hbm_peak()
     nlaunch = max(1, int(st["batches"]))

@@ -60,14 +60,15 @@ struct BandSmem
 /* column x owns 32 slots; its rows are rotated by 2x so that one row of the band's 8 columns lands on 8 different bank pairs */
 __device__ __forceinline__ int band_slot(int xl, int yl) { return xl * TH + ((yl + 2 * xl) & 31); }
 
-/* Queue ticket for ONE lane.  Spelled as PTX: atomicAdd() under `if(lane == 0)` is turned by the compiler into its warp-aggregated
- * form (vote, leader atomic, SHFL of the result), and that shuffle waits for the atomic's round trip on the spot -- the capture showed
- * 13 % of the kernel's stall samples there.  This way the ticket is only waited for where it is used: at the top of the NEXT item. */
-__device__ __forceinline__ int queue_ticket(int* counter, int n)
+/* Queue ticket for ONE lane: the counter's value before it is incremented by one.  atomicAdd() -- and equally a PTX `atom.add` -- on a
+ * warp-uniform address is turned by ptxas into its warp-aggregated form (vote, leader atomic, SHFL of the result), and that shuffle waits
+ * for the atomic's round trip on the spot: the capture showed 6 % of the kernel's stall samples on the two tickets that are meant to be
+ * fetched one item AHEAD.  `atom.inc` is left alone, and its result is only waited for where it is used: at the top of the next item. */
+__device__ __forceinline__ int queue_ticket(int* counter)
 {
-    int old;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(n) : "memory");
-    return old;
+    unsigned old;
+    asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "l"(counter) : "memory");
+    return (int) old;
 }
 
 template<bool HASH>
@@ -92,7 +93,7 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
 
     /* lane 0 owns the warp's queue cursors: the atomics for the NEXT item are issued when the current one starts */
     int g_next = 0, c_next = 0;
-    if(lane == 0) { g_next = queue_ticket(p.work_counter, 1); c_next = queue_ticket(p.work_counter + 1, BAND_CLEAR); }
+    if(lane == 0) { g_next = queue_ticket(p.work_counter); c_next = queue_ticket(p.work_counter + 1) * BAND_CLEAR; }
 
     for(;;)
     {
@@ -103,12 +104,12 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
             for(int base = c0; base < nclear; )
             {
                 reset_untouched_tiles<HASH>(p, base, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
-                if(lane == 0) base = queue_ticket(p.work_counter + 1, BAND_CLEAR);
+                if(lane == 0) base = queue_ticket(p.work_counter + 1) * BAND_CLEAR;
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
             }
             break;
         }
-        if(lane == 0) { g_next = queue_ticket(p.work_counter, 1); c_next = queue_ticket(p.work_counter + 1, BAND_CLEAR); }
+        if(lane == 0) { g_next = queue_ticket(p.work_counter); c_next = queue_ticket(p.work_counter + 1) * BAND_CLEAR; }
         reset_untouched_tiles<HASH>(p, c0, 1, BAND_CLEAR, lane, pat_pixel, pat_z);
 
         const uint32_t item = __ldg(p.lit_list + g / BANDS);

@@ -21,6 +21,7 @@
 #define GEL_DIRECT_CUH
 
 #include "gel_kernels.cuh"
+#include <type_traits>
 
 namespace gelk {
 
@@ -85,16 +86,22 @@ struct DirectParams
     int tpw;                       /* triangles per warp of D1 / D3 for this batch (power of two) */
 };
 
-struct DirectScratch               /* per warp */
+/* per warp.  The parked pass (PHASE 1) also keeps a ring of hi-Z survivors; the near pass has no use for it, and without it a one-warp
+ * CTA needs 4 224 + 1 024 bytes of shared memory: 32 CTAs per SM fit the 164 KB carve-out exactly, which leaves 92 KB of the SM's 256 KB
+ * to L1 (the gathers' hit rate), against 60 KB with the 196 KB carve-out the common layout needed. */
+struct DirectCand { uint32_t cand[DIRECT_CAND]; };   /* triangle ids */
+struct DirectNoCand {};
+template<int PHASE>
+struct DirectScratchT : std::conditional<PHASE == 1, DirectCand, DirectNoCand>::type
 {
     float4 slab[4][32];                  /* q0 .. q3 of the current 32 triangles (gel_kernels.cuh, slab layout) */
     uint32_t unit[DIRECT_UNIT_WINDOW];   /* lane << 13 | x */
-    uint32_t cand[DIRECT_CAND];          /* triangle ids */
     float2 q_n[QCAP];
     uint32_t q_id[QCAP];                 /* lane << 26 | x << 13 | y */
     uint32_t bx[32], by[32];             /* x0 | x1 << 16 ;  y0 | y1 << 13 | guard << 26 */
     float den_hi[32];
 };
+static_assert(sizeof(DirectScratchT<0>) == 4224 && sizeof(DirectScratchT<1>) == 5248, "shared-memory budget of the direct raster kernels (carve-out fits)");
 
 /* L2 cache-policy hints (sm_80+ createpolicy; on sm_100a the policy rides in the memory descriptor, no extra
  * instruction per access).  The fill's 51 MB per frame of write-once stores are marked evict-first and the key buffer's
@@ -196,8 +203,8 @@ direct_hiz_kernel(DirectParams p)
 
 /* D1 / D3 ------------------------------------------------------------------------------------------------------- */
 
-template<bool HINT>
-__device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned long long* keys, DirectScratch& ws, int i, uint64_t pol)
+template<bool HINT, class Scratch>
+__device__ __forceinline__ void direct_resolve(const DirectParams& p, unsigned long long* keys, Scratch& ws, int i, uint64_t pol)
 {
     const uint32_t id = ws.q_id[i];
     const float2 n = ws.q_n[i];
@@ -210,11 +217,11 @@ template<int PHASE, bool HINT>
 __global__ void __launch_bounds__(DIRECT_THREADS, GEL_DIRECT_MINB)
 direct_raster_kernel(DirectParams p)
 {
-    __shared__ DirectScratch scratch[DIRECT_WARPS];
+    __shared__ DirectScratchT<PHASE> scratch[DIRECT_WARPS];
     const uint64_t pol = HINT ? l2_policy_evict_last() : 0ull;
     const int view = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    DirectScratch& ws = scratch[warp];
+    DirectScratchT<PHASE>& ws = scratch[warp];
     const float4* xf = p.xf + (size_t) view * p.nuniq;
     unsigned long long* keys = p.keys + (size_t) view * p.xres * p.yres;
     uint4* far = p.far + (size_t) view * p.ntri;
@@ -234,7 +241,7 @@ direct_raster_kernel(DirectParams p)
         bool have = false, park = false;
         uint32_t tri = 0, pbx = 0, pby = 0, bound = 0;
         float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-        if(PHASE == 0)
+        if constexpr(PHASE == 0)
         {
             if(tnext >= last) break;
             const int t = tnext + lane;

@@ -109,7 +109,7 @@ __host__ __device__ __forceinline__ bool region_from_stats(const uint32_t* s, in
 constexpr int XF_PER_THREAD = 4;     /* vertices per thread: amortises the per-warp reductions of the view statistics */
 
 __global__ void __launch_bounds__(256)
-transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict__ vpos,
+transform_kernel(const float4* __restrict__ vconst, const float4* __restrict__ vpos,
                  const float4* __restrict__ vnrm, float4* __restrict__ xf, uint32_t* __restrict__ vstat, int nuniq, int xres, int yres)
 {
     __shared__ uint32_t s_lo, s_hi;
@@ -117,7 +117,14 @@ transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict_
     const int view = blockIdx.y;
     if(threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
     __syncthreads();
-    const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + view), xres, yres);
+    /* the view's constants (basis rows, vdot(row, eye), viewport scale / offset: main.c:375-377, 290-293) were computed once per view by
+     * batch_init_kernel -- view_const() per thread was a sixth of this kernel's instructions (four div.rn + three dot products) */
+    gel::ViewConst c;
+    {
+        const float4 c0 = __ldg(vconst + 4 * view), c1 = __ldg(vconst + 4 * view + 1), c2 = __ldg(vconst + 4 * view + 2), c3 = __ldg(vconst + 4 * view + 3);
+        c.xx = c0.x; c.xy = c0.y; c.xz = c0.z; c.yx = c0.w; c.yy = c1.x; c.yz = c1.y; c.zx = c1.z; c.zy = c1.w;
+        c.zz = c2.x; c.xe = c2.y; c.ye = c2.z; c.ze = c2.w; c.w = c3.x; c.h = c3.y; c.x0 = c3.z; c.y0 = c3.w;
+    }
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
     int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
     #pragma unroll
@@ -159,7 +166,8 @@ transform_kernel(const gelcu_view* __restrict__ views, const float4* __restrict_
  * and, for the tile pipeline, chain heads (-1), lit flags and the two work queues. */
 __global__ void __launch_bounds__(256)
 batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint32_t* __restrict__ flags, unsigned long long* __restrict__ hash,
-                  int* __restrict__ heads, int* __restrict__ tile_lit, int* __restrict__ work, int nviews, int ntiles, int want_hash)
+                  int* __restrict__ heads, int* __restrict__ tile_lit, int* __restrict__ work, int nviews, int ntiles, int want_hash,
+                  const gelcu_view* __restrict__ views, float4* __restrict__ vconst, int xres, int yres)
 {
     const size_t i0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
     if(i0 < (size_t) nviews)
@@ -171,6 +179,10 @@ batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint3
         cursors[4 * i0] = 0; cursors[4 * i0 + 1] = 0; cursors[4 * i0 + 2] = 0; cursors[4 * i0 + 3] = 0;
         flags[i0] = 0u;
         if(want_hash) { hash[2 * i0] = 0ull; hash[2 * i0 + 1] = 0ull; }
+        /* the view's constants for K1 (same operations as ever: gel::view_const) */
+        const gel::ViewConst c = gel::view_const(reinterpret_cast<const float*>(views + i0), xres, yres);
+        vconst[4 * i0] = make_float4(c.xx, c.xy, c.xz, c.yx); vconst[4 * i0 + 1] = make_float4(c.yy, c.yz, c.zx, c.zy);
+        vconst[4 * i0 + 2] = make_float4(c.zz, c.xe, c.ye, c.ze); vconst[4 * i0 + 3] = make_float4(c.w, c.h, c.x0, c.y0);
     }
     if(heads)
     {

@@ -64,7 +64,7 @@ struct gelcu_ctx
     uint32_t* d_tex = nullptr; int tw = 0, th = 0;
     /* per-batch work buffers */
     int batch_opt = 0, batch = 0, cap_e = 0, cap_d = 0, ctas_per_sm = 1024 / RASTER_THREADS, stage_timing = 1;
-    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr; uint32_t* d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr; float4* d_vrec = nullptr;   /* d_vrec: per-(view, triangle) records K2 leaves for K3 */
+    float4* d_xf = nullptr; uint32_t* d_entries = nullptr; uint4* d_descs = nullptr; int *d_heads = nullptr, *d_cursors = nullptr, *d_tile_lit = nullptr; uint32_t* d_lit_list = nullptr; uint32_t* d_vstat = nullptr; uint4* d_far = nullptr; float4* d_vrec = nullptr; float4* d_vconst = nullptr;   /* d_vconst: [view][4] per-view constants of K1 */   /* d_vrec: per-(view, triangle) records K2 leaves for K3 */
     /* direct pipeline */
     unsigned long long* d_keys = nullptr; uint32_t* d_hiz = nullptr; uint4* d_parked = nullptr; int *d_far_count = nullptr, *d_region = nullptr; int hbx = 0, hby = 0;
     int pipeline_opt = 0, pipeline_auto = 1, work_pipeline = 0;   /* 0 auto, 1 tile, 2 direct */
@@ -97,7 +97,7 @@ void free_bins(gelcu_ctx* c)
 void free_work(gelcu_ctx* c)
 {
     free_bins(c);
-    dfree(c->d_xf); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_vrec); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
+    dfree(c->d_xf); dfree(c->d_heads); dfree(c->d_cursors); dfree(c->d_tile_lit); dfree(c->d_lit_list); dfree(c->d_vstat); dfree(c->d_far); dfree(c->d_vrec); dfree(c->d_vconst); dfree(c->d_keys); dfree(c->d_hiz); dfree(c->d_parked); dfree(c->d_far_count); dfree(c->d_region);
     dfree(c->d_flags); dfree(c->d_hash); dfree(c->d_work);
     dfree(c->d_pixel[0]); dfree(c->d_pixel[1]); dfree(c->d_z[0]); dfree(c->d_z[1]); dfree(c->d_rgb[0]); dfree(c->d_rgb[1]);
     c->batch = 0;
@@ -168,6 +168,7 @@ int ensure_work(gelcu_ctx* c, int B, int cap_e, int cap_d)
         const size_t frame = (size_t) c->xres * c->yres;
         CU(cudaMalloc(&c->d_xf, sizeof(float4) * std::max<size_t>(1, (size_t) B * c->nuniq)));
         CU(cudaMalloc(&c->d_vstat, sizeof(uint32_t) * VIEW_STAT_WORDS * B));
+        CU(cudaMalloc(&c->d_vconst, sizeof(float4) * 4 * B));
         CU(cudaMalloc(&c->d_flags, sizeof(uint32_t) * B));
         CU(cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 2 * B));
         CU(cudaMalloc(&c->d_cursors, sizeof(int) * 4 * B));
@@ -228,13 +229,13 @@ int enqueue_batch(gelcu_ctx* c, int first, int n, int buf, bool want_hash, bool 
         const size_t cells = pipe != 2 ? (size_t) n * c->ntiles * NCHAIN : (size_t) n;
         const int grid = (int) std::min<size_t>((size_t) c->num_sms * 8, std::max<size_t>(1, (cells / 4 + 255) / 256));
         batch_init_kernel<<<grid, 256, 0, s>>>(c->d_vstat, c->d_cursors, c->d_flags, c->d_hash, pipe != 2 ? c->d_heads : nullptr, c->d_tile_lit, c->d_work,
-                                               n, c->ntiles, want_hash ? 1 : 0);
+                                               n, c->ntiles, want_hash ? 1 : 0, c->d_views + first, c->d_vconst, c->xres, c->yres);
         c->stats.kernels_launched++;
     }
     if(ev) CU(cudaEventRecord(ev[0], s));
     if(c->nuniq > 0)
     {
-        transform_kernel<<<dim3((c->nuniq + 256 * XF_PER_THREAD - 1) / (256 * XF_PER_THREAD), n), 256, 0, s>>>(c->d_views + first, c->d_vpos, c->d_vnrm, c->d_xf, c->d_vstat, c->nuniq, c->xres, c->yres);
+        transform_kernel<<<dim3((c->nuniq + 256 * XF_PER_THREAD - 1) / (256 * XF_PER_THREAD), n), 256, 0, s>>>(c->d_vconst, c->d_vpos, c->d_vnrm, c->d_xf, c->d_vstat, c->nuniq, c->xres, c->yres);
         c->stats.kernels_launched++;
     }
     if(ev) CU(cudaEventRecord(ev[1], s));
@@ -678,12 +679,28 @@ int gelcu_set_option(gelcu_ctx* c, const char* name, int value)
     else if(!strcmp(name, "batch_views")) { if(value < 0) return fail(GELCU_E_INVALID, "batch_views < 0"); c->batch_opt = value; cudaSetDevice(c->device); sync_ctx(c); free_work(c); }
     else if(!strcmp(name, "tma_reset")) c->tma_reset = value ? 1 : 0;
     else if(!strcmp(name, "raster_mode")) { if(value < 0 || value > 1) return fail(GELCU_E_INVALID, "raster_mode must be 0 (a CTA per tile) or 1 (a warp per band)"); c->raster_mode = value; }
-    else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; }
+    else if(!strcmp(name, "raster_ctas_per_sm")) { if(value < 1 || value > 16) return fail(GELCU_E_INVALID, "raster_ctas_per_sm out of [1,16]"); c->ctas_per_sm = value; c->band_ctas_per_sm = value; }
+    else if(!strcmp(name, "band_carveout"))
+    {
+        /* shared-memory carve-out hint (percent of 228 KB, -1 = driver default) of the band rasteriser: 8 CTAs per SM need the 228 KB carve-out (28 KB of L1), 7 fit 196 KB (60 KB of L1) */
+        if(value < -1 || value > 100) return fail(GELCU_E_INVALID, "band_carveout out of [-1,100]");
+        cudaSetDevice(c->device);
+        CU(cudaFuncSetAttribute(raster_band_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CU(cudaFuncSetAttribute(raster_band_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+    }
     else if(!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if(!strcmp(name, "compact_records")) c->allow_compact = value != 0;      /* takes effect at the next gelcu_set_mesh */
     else if(!strcmp(name, "fill_mode")) { if(value < 0 || value > 5) return fail(GELCU_E_INVALID, "fill_mode must be 0..5"); c->fill_mode = value; }
     else if(!strcmp(name, "fill_ctas_per_sm")) { if(value < 1 || value > 8) return fail(GELCU_E_INVALID, "fill_ctas_per_sm out of [1,8]"); c->fill_ctas = value; }
     else if(!strcmp(name, "red_hint")) c->red_hint = value != 0;
+    else if(!strcmp(name, "near_carveout"))
+    {
+        /* shared-memory carve-out hint (percent of 228 KB, -1 = driver default) of the direct pipeline's near pass: the kernel needs 164 KB at 32 CTAs per SM; what the carve-out leaves is L1 */
+        if(value < -1 || value > 100) return fail(GELCU_E_INVALID, "near_carveout out of [-1,100]");
+        cudaSetDevice(c->device);
+        CU(cudaFuncSetAttribute(direct_raster_kernel<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+        CU(cudaFuncSetAttribute(direct_raster_kernel<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+    }
     else if(!strcmp(name, "fill_after")) { if(value < 0 || value > 2) return fail(GELCU_E_INVALID, "fill_after must be 0, 1 or 2"); c->fill_after = value; }
     else if(!strcmp(name, "store_hint")) { if(value < 0 || value > 3) return fail(GELCU_E_INVALID, "store_hint must be 0..3 (bit 0: fill stores, bit 1: resolve stores evict-first)"); c->store_hint = value; }
     else if(!strcmp(name, "fill_sleep_ns")) { if(value < 0 || value > 1000000) return fail(GELCU_E_INVALID, "fill_sleep_ns out of [0, 1000000]"); c->fill_sleep_ns = value; }

@@ -147,7 +147,11 @@ int gelcu_read_frame(gelcu_ctx* ctx, int slot, uint32_t* pixel_out, float* z_out
  *   "graph_small_calls"  1 (default) = calls of up to 4 views replay a captured CUDA graph (one launch instead of ~20 API calls:
  *                   the interactive one-view-per-frame use); stage timings are not recorded for such calls
  *   "fill_mode", "fill_ctas_per_sm", "fill_sleep_ns", "red_hint", "store_hint"   direct pipeline experiments with the background
- *                   reset and L2 cache-policy hints (defaults: plain trailing fill, evict-last hint on the key REDs) */
+ *                   reset and L2 cache-policy hints (defaults: plain trailing fill, evict-last hint on the key REDs)
+ *   "raster_mode"   tile pipeline: 1 (default) = a warp per band (raster_band_kernel), 0 = a CTA per tile (raster_kernel)
+ *   "tma_reset"     tile pipeline: 1 (default) = untouched tiles are reset by TMA tensor stores, 0 = by a store loop
+ *   "near_carveout", "band_carveout"   shared-memory carve-out hint (percent, -1 = driver default) of the direct pipeline's near pass / the
+ *                   band rasteriser: measurement knobs (profiles/README.md, session 3); the defaults are the fastest */
 int gelcu_set_option(gelcu_ctx* ctx, const char* name, int value);
 int gelcu_get_stats(gelcu_ctx* ctx, gelcu_stats* out);
 

@@ -13,9 +13,10 @@ cap cfg3 64 direct_raster_kernel r02_d1 6 2
 cap cfg3 64 direct_resolve_kernel r02_d5 3 1
 cap cfg3 64 direct_fill_kernel r02_d5a 3 1
 cap cfg3 64 direct_hiz_kernel r02_d2 3 1
+cap cfg3 64 direct_clear_kernel r02_d0 3 1
 cap cfg3 64 transform_kernel r02_transform_cfg3 3 1
-cap cfg5 64 raster_kernel r02_raster_cfg5 3 1
+cap cfg5 64 raster_band_kernel r02_raster_cfg5 3 1
 cap cfg5 64 bin_kernel r02_bin_cfg5 3 1
-cap cfg2 64 raster_kernel r02_raster_cfg2 3 1
-cap cfg1 64 raster_kernel r02_raster_cfg1 3 1
+cap cfg2 64 raster_band_kernel r02_raster_cfg2 3 1
+cap cfg1 64 raster_band_kernel r02_raster_cfg1 3 1
 ls -la gpurun_out/r02_*.ncu-rep

@@ -39,8 +39,8 @@ for src, dst in (("r02_bench_cfg3.json", "r02_bench_cfg3.json"), ("r02_bench_ref
 
 def per_frame(cap, pick=0): r = traffic[cap][pick]; return int((r[1] + r[2]) / 64), f"{r[1] / 1e6:.1f} MB read + {r[2] / 1e6:.1f} MB written over 64 frames"
 recs = []
-for kernel, wl, cap, txt in (("direct_raster_kernel<0>", "cfg3", "r02_d1", "r02_ncu_d1.txt"), ("raster_kernel", "cfg5", "r02_raster_cfg5", "r02_ncu_raster_cfg5.txt"),
-                             ("raster_kernel", "cfg2", "r02_raster_cfg2", "r02_ncu_raster_cfg2.txt"), ("raster_kernel", "cfg1", "r02_raster_cfg1", "r02_ncu_raster_cfg1.txt")):
+for kernel, wl, cap, txt in (("direct_raster_kernel<0>", "cfg3", "r02_d1", "r02_ncu_d1.txt"), ("raster_band_kernel", "cfg5", "r02_raster_cfg5", "r02_ncu_raster_cfg5.txt"),
+                             ("raster_band_kernel", "cfg2", "r02_raster_cfg2", "r02_ncu_raster_cfg2.txt"), ("raster_band_kernel", "cfg1", "r02_raster_cfg1", "r02_ncu_raster_cfg1.txt")):
     if cap in traffic:
         b, how = per_frame(cap); recs.append({"kernel": kernel, "workload": wl, "bytes_per_frame": b, "from": f"{txt}: {how}"})
 whole = sum((r + w) for cap in ("r02_transform_cfg3", "r02_d1", "r02_d5a", "r02_d2", "r02_d5") if cap in traffic for _, r, w in traffic[cap]) / 64
