@@ -51,7 +51,7 @@ WORKLOADS = {
     "cfg1": ("sphere", 50, 256, 800, 600, 64, "5 000-tri sphere + 256^2 texture @ 800x600 (the reference's window)"),
     "cfg2": ("sphere", 50, 256, 1920, 1080, 360, "5 000-tri sphere + 256^2 texture, 360 rotated views @ 1920x1080"),
     "cfg3": ("sphere", 707, 2048, 3840, 2160, 64, "999 698-tri sphere + 2048^2 texture @ 3840x2160 (HBM-roofline case)"),
-    "cfg4": ("overdraw", 100_000, 256, 1920, 1080, 8, "200 000 small overlapping tris (z ties) @ 1920x1080"),
+    "cfg4": ("overdraw", 100_000, 256, 1920, 1080, 64, "200 000 small overlapping tris (z ties) @ 1920x1080"),
     "cfg5": ("sphere", 50, 256, 1920, 1080, 8192, "5 000-tri sphere, 8192 rotated views @ 1920x1080 sharded over the GPUs"),
 }
 SWEEP = {"cfg1": 64, "cfg2": 360, "cfg3": 64, "cfg5": 8192}          # views of the workload's full rotation, xt_k = 2 pi k / n

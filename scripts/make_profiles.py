@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import bench
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 HEAD = "# ncu --set full --clock-control none --import-source on  (scripts/gpu_r2_evidence.sh), summarised by scripts/ncu_summary.py + scripts/ncu_lines.py\n"
-CAPS = {"r02_d1": "r02_ncu_d1.txt", "r02_d5": "r02_ncu_d5.txt", "r02_d5a": "r02_ncu_d5a.txt", "r02_d2": "r02_ncu_d2.txt", "r02_transform_cfg3": "r02_ncu_transform_cfg3.txt",
+CAPS = {"r02_d1": "r02_ncu_d1.txt", "r02_d5": "r02_ncu_d5.txt", "r02_d5a": "r02_ncu_d5a.txt", "r02_d2": "r02_ncu_d2.txt", "r02_d0": "r02_ncu_d0.txt", "r02_transform_cfg3": "r02_ncu_transform_cfg3.txt",
         "r02_raster_cfg5": "r02_ncu_raster_cfg5.txt", "r02_bin_cfg5": "r02_ncu_bin_cfg5.txt", "r02_raster_cfg2": "r02_ncu_raster_cfg2.txt", "r02_raster_cfg1": "r02_ncu_raster_cfg1.txt"}
 
 

@@ -643,6 +643,28 @@ def test_direct_pipeline_fill_variants(opts):
                 assert not hashes or np.array_equal(out["hash"], ref["hash"])
 
 
+@pytest.mark.parametrize("opts", [{}, {"near_carveout": 100}, {"band_carveout": 85, "raster_ctas_per_sm": 7}, {"raster_mode": 0}])
+def test_session3_knobs_leave_the_frames_alone(opts):
+    """Round 2, session 3: the shared-memory carve-out hints and the CTA-per-tile rasteriser (a call of four batches, both frame
+    buffers, copies overlapping renders) -- the reference's frames, through the whole-frame and the region entry points."""
+    rng = np.random.default_rng(7707)
+    tv, tn, tt = random_soup(rng, 1200, size=(0.01, 0.2), xr=(-0.4, 0.4), yr=(0.1, 0.9), zspread=0.4)
+    tex = small_tex(rng, 32, 32)
+    W, H = 320, 200
+    bases = gel_b200.view_bases([(0.21 * k, 0.01 * k) for k in range(30)])
+    ref = oracle.render_views(tv, tn, tt, tex, W, H, bases, nthreads=NTHREADS, z=True)
+    with make_renderer(W, H, tv, tn, tt, tex) as r:
+        for k, v in opts.items():
+            r.set_option(k, v)
+        out = r.render(bases, z=True)
+        assert np.array_equal(out["pixel"], ref["pixel"]) and np.array_equal(bits(out["z"]), bits(ref["z"])), opts
+        assert r.stats()["batches"] == 4
+        canvas = np.full((len(bases), W * H), 0xDEADBEEF, np.uint32)
+        rects = np.zeros((len(bases), 4), np.int32); rects[:] = (0, 0, W - 1, H - 1)        # garbage everywhere: everything may be stale
+        r.render_region(bases, canvas, rects)
+        assert np.array_equal(canvas, ref["pixel"]), opts
+
+
 def test_call_order_and_argument_errors():
     r = gel_b200.Renderer(64, 64)
     with pytest.raises(gel_b200.GelcuError) as e:
