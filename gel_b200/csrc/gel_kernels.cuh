@@ -203,7 +203,7 @@ batch_init_kernel(uint32_t* __restrict__ vstat, int* __restrict__ cursors, uint3
  * 8 x 16 bytes = one 128-byte line per triangle, so whatever part a consumer needs arrives with one L2 request:
  *   0  ax, ay, v0x, v0y            1  v1x, v1y, k0, k1           2  d00, d01, d11, den (sign-normalised, den > 0)
  *   3  az, bz, cz, ~tri            4  bbox x0 | x1 << 16, y0 | y1 << 16 (clipped to the frame), flags (1 drawable, 2 guard), zmax
- *   5  shade a, b, c, -            6  ta.x, ta.y, tb.x, tb.y     7  tc.x, tc.y, -, -
+ *   5  shade a, b, c, -            6  ta.x, ta.y, tb.x, tb.y     7  tc.x, tc.y, e_v, e_w (slack terms of the band rasteriser's row trimming: gel_math.h, trim_slack)
  * Same operations on the same operands as before (gel::tri_setup), so the frames do not change by a bit. */
 constexpr int VREC_QUADS = 8;
 
