@@ -26,6 +26,10 @@
 
 namespace gelk {
 
+#ifndef GEL_BAND_MERGE
+#define GEL_BAND_MERGE 0                          /* depth merge of a flush: 0 = store + re-check (two survivors of one flush on one pixel race, the larger key stores again);
+                                                   * 1 = MATCH.ANY on the slot, atomic only on such a conflict: race-free under compute-sanitizer, same frames, -4.5 % */
+#endif
 #ifndef GEL_BAND_ROW_TRIM
 #define GEL_BAND_ROW_TRIM 1                       /* per-column exact row trimming in the unit prologue (0 = walk the bbox rows) */
 #endif
@@ -147,8 +151,22 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
                 key = fragment_key(n.x, n.y, ws.slab[2][src].w, ws.slab[3][src]);
                 k = ws.keys + band_slot((int) ((id >> 5) & 31), (int) (id & 31));
             }
-            /* only this warp writes these keys: load / compare / store, again while two survivors of this flush share a pixel
-             * (one of the racing stores lands; the slot only ever grows, so a lane whose key is still larger stores once more) */
+#if GEL_BAND_MERGE == 1
+            /* Only this warp writes these keys, so the depth merge needs no atomic: load, compare, store.  Two survivors of one flush
+             * can still share a pixel (neighbouring triangles on their common edge, overdraw inside a batch): MATCH.ANY on the slot
+             * finds that, and only then the warp goes through the atomic (a compare-and-swap loop on sm_100; rare). */
+            const bool pending = key > *k;
+            __syncwarp();                                                 /* every lane has read its slot before any lane writes one */
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, pending ? (uint32_t) (k - ws.keys) : 0x10000u + (uint32_t) lane);
+            if(__any_sync(0xFFFFFFFFu, (peers & (peers - 1)) != 0u))
+            { if(pending) atomicMax(k, key); }
+            else if(pending) *k = key;
+#else
+            /* Only this warp writes these keys: load / compare / store, again while two survivors of this flush share a pixel.  That is
+             * a deliberate intra-warp write-write race (compute-sanitizer's racecheck reports it): each lane's 64-bit store is one
+             * aligned access, so one of the racing keys lands whole; every lane then re-reads its slot, and a lane whose key is still
+             * larger stores once more -- the slot only ever grows, so the loop ends with the maximum in place (almost always after one
+             * round).  GEL_BAND_MERGE=1 is the race-free spelling. */
             bool pending = key > *reinterpret_cast<volatile unsigned long long*>(k);
             while(__any_sync(0xFFFFFFFFu, pending))
             {
@@ -157,6 +175,7 @@ raster_band_kernel(const __grid_constant__ RasterParams p)
                 pending = pending && key > *reinterpret_cast<volatile unsigned long long*>(k);
                 __syncwarp();
             }
+#endif
             __syncwarp();                                                 /* the stack slots just read may be pushed on again */
         };
 
