@@ -477,8 +477,10 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, const float4
     uint32_t ia, ib, ic, uvw[6];
     if(COMPACT)
     {
-        const uint4* rec = p.trec + 2 * (size_t) tri;
-        const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        float4 f0, f1;
+        ldg256(p.trec + 2 * (size_t) tri, f0, f1);                       /* the 32-byte record in one request */
+        const uint4 r0 = make_uint4(__float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f0.z), __float_as_uint(f0.w));
+        const uint4 r1 = make_uint4(__float_as_uint(f1.x), __float_as_uint(f1.y), __float_as_uint(f1.z), __float_as_uint(f1.w));
         const uint32_t m = (1u << TREC_COMPACT_BITS) - 1u;
         ia = r0.x & m; ib = (r0.x >> 21 | r0.y << 11) & m; ic = (r0.y >> 10) & m;
         uvw[0] = r0.z; uvw[1] = r0.w; uvw[2] = r1.x; uvw[3] = r1.y; uvw[4] = r1.z; uvw[5] = r1.w;
@@ -486,7 +488,11 @@ __device__ __forceinline__ void direct_shade(const DirectParams& p, const float4
     else
     {
         const uint4* rec = p.trec + (size_t) TREC_QUADS * tri;
-        const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        float4 f0, f1;
+        ldg256(rec, f0, f1);
+        const uint4 r0 = make_uint4(__float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f0.z), __float_as_uint(f0.w));
+        const uint4 r1 = make_uint4(__float_as_uint(f1.x), __float_as_uint(f1.y), __float_as_uint(f1.z), __float_as_uint(f1.w));
+        const uint4 r2 = __ldg(rec + 2);
         ia = r0.x; ib = r0.y; ic = r0.z;
         uvw[0] = r1.x; uvw[1] = r1.y; uvw[2] = r1.z; uvw[3] = r1.w; uvw[4] = r2.x; uvw[5] = r2.y;
     }

@@ -86,6 +86,25 @@ constexpr unsigned long long CLEAR_KEY = (0x00800000ull << 32) | 0xFFFFFFFFull; 
 constexpr uint32_t FLAG_CLIPPED = 1u, FLAG_TEXCLAMP = 2u, FLAG_OVERFLOW = 0x80000000u;
 constexpr float GUARD_EPS = 1e-20f, GUARD_DEN_MAX = 1e18f, U_SLACK = 1.00001f;
 
+/* 32 bytes in one request (sm_100: ld.global.nc.v8, SASS LDG.E.ENL2.256): a 32-byte-aligned pair of quads costs the L1 one sector
+ * lookup instead of two.  `p` must be 32-byte aligned.  Used by the direct pipeline's resolve pass, which is bound by L1 sector
+ * lookups (its 32-byte triangle record: l1tex__t_sectors -14 %, the kernel -3.6 %); in the band rasteriser, which is not, the same
+ * loads measured -0.4 % and stayed 128-bit. */
+#ifndef GEL_LD256
+#define GEL_LD256 1
+#endif
+__device__ __forceinline__ void ldg256(const void* p, float4& lo, float4& hi)
+{
+#if GEL_LD256
+    uint32_t a, b, c, d, e, f, g, h;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p));
+    lo = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+    hi = make_float4(__uint_as_float(e), __uint_as_float(f), __uint_as_float(g), __uint_as_float(h));
+#else
+    lo = __ldg(reinterpret_cast<const float4*>(p)); hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* K1: vertex transform                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
