@@ -48,9 +48,6 @@ constexpr int DIRECT_WARPS = DIRECT_THREADS / 32;
 #ifndef GEL_DIRECT_TPW
 #define GEL_DIRECT_TPW 1024
 #endif
-#ifndef GEL_RESOLVE_IDX32
-#define GEL_RESOLVE_IDX32 1        /* resolve pass addressing: 0 = per-view base pointers + 32-bit offsets, 1 = one 32-bit element index per pixel, 2 = 1 with restrict bases */
-#endif
 #ifndef GEL_TRIM_ROUNDS
 #define GEL_TRIM_ROUNDS 1          /* rounds of exact bbox trimming per rasterised triangle (0 = off) */
 #endif
@@ -87,8 +84,8 @@ struct DirectParams
 };
 
 /* per warp.  The parked pass (PHASE 1) also keeps a ring of hi-Z survivors; the near pass has no use for it, and without it a one-warp
- * CTA needs 4 224 + 1 024 bytes of shared memory: 32 CTAs per SM fit the 164 KB carve-out exactly, which leaves 92 KB of the SM's 256 KB
- * to L1 (the gathers' hit rate), against 60 KB with the 196 KB carve-out the common layout needed. */
+ * CTA needs 4 224 + 1 024 bytes of shared memory: 32 CTAs per SM fit the 164 KB carve-out exactly (the common layout needed the 196 KB
+ * one; a carve-out beyond the kernel's need costs the step 2 %: profiles/README.md, session 3). */
 struct DirectCand { uint32_t cand[DIRECT_CAND]; };   /* triangle ids */
 struct DirectNoCand {};
 template<int PHASE>
@@ -705,16 +702,12 @@ direct_resolve_kernel(DirectParams p)
     uint32_t* vflags = p.flags + view;
     const float twm1 = gel::i2f(p.tw - 1), thm1 = gel::i2f(p.th - 1);     /* (float) (w - 1), (float) (h - 1) of main.c:360-361, converted once */
     const int nstrips = (rx1 - rx0 + 8) / 8;
-#if GEL_RESOLVE_IDX32
-    /* Addressing variant: a pixel is ONE 32-bit element index into the batch's buffers (view * frame + x * yres + y; the host keeps
-     * views-per-batch * frame and views-per-batch * distinct vertices below 2^32), scaled onto the buffer bases. */
+    /* Addressing: a pixel is ONE 32-bit element index into the batch's buffers (view * frame + x * yres + y; the host keeps
+     * views-per-batch * frame and views-per-batch * distinct vertices below 2^32), scaled onto the buffer bases.  With per-view 64-bit
+     * base pointers the 32-register budget made ptxas rebuild them in every iteration (45 of the loop's 196 instructions). */
     const uint32_t frame = (uint32_t) p.xres * (uint32_t) p.yres;
     const uint32_t fbase = (uint32_t) view * frame, vbase = (uint32_t) view * (uint32_t) p.nuniq;
-#if GEL_RESOLVE_IDX32 == 2
-    unsigned long long* __restrict__ bkeys = p.keys; uint32_t* __restrict__ bpixel = p.pixel; float* __restrict__ bz = p.zbuf; const float4* __restrict__ bxf = p.xf;
-#else
     unsigned long long* bkeys = p.keys; uint32_t* bpixel = p.pixel; float* bz = p.zbuf; const float4* bxf = p.xf;
-#endif
     for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     {
         const int x = rx0 + strip * 8 + px;
@@ -734,33 +727,6 @@ direct_resolve_kernel(DirectParams p)
             if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
         }
     }
-#else
-    /* per-view bases live outside the pixel loop; inside it everything is a 32-bit offset from them */
-    const size_t frame = (size_t) p.xres * p.yres;
-    unsigned long long* __restrict__ vkeys = p.keys + (size_t) view * frame;
-    uint32_t* __restrict__ vpixel = p.pixel + (size_t) view * frame;
-    float* __restrict__ vz = p.zbuf + (size_t) view * frame;
-    const float4* __restrict__ xf = p.xf + (size_t) view * p.nuniq;
-    for(int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
-    {
-        const int x = rx0 + strip * 8 + px;
-        if(x > rx1) continue;
-        /* per-view bases are CTA-uniform; inside the frame a 32-bit unsigned offset addresses every pixel (<= 2^26) */
-        uint32_t off = (uint32_t) x * (uint32_t) p.yres + (uint32_t) (ry0 + py);
-        unsigned long long next_key = ry0 + py <= ry1 ? vkeys[off] : CLEAR_KEY;
-        for(int y = ry0 + py; y <= ry1; y += CTA_ROWS, off += CTA_ROWS)
-        {
-            const unsigned long long key = next_key;
-            if(y + CTA_ROWS <= ry1) next_key = vkeys[off + CTA_ROWS];         /* one iteration ahead of its use */
-            uint32_t colour; float z;
-            direct_shade<COMPACT>(p, xf, 0u, vflags, twm1, thm1, key, x, y, colour, z);
-            st_b64<HINT>(vkeys + off, CLEAR_KEY, pol);                    /* the buffer is all "no winner" again for the next batch */
-            st_b32<HINT>(vpixel + off, colour, pol);
-            st_b32<HINT>(vz + off, __float_as_uint(z), pol);
-            if(HASH) { hp += gel::salt_mix(colour, off); hz += gel::salt_mix(__float_as_uint(z), off); }
-        }
-    }
-#endif
     if(HASH)
     {
         for(int d = 16; d; d >>= 1) { hp += __shfl_xor_sync(0xFFFFFFFFu, hp, d); hz += __shfl_xor_sync(0xFFFFFFFFu, hz, d); }
