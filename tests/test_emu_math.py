@@ -147,6 +147,30 @@ def test_row_trim_never_removes_a_row_that_could_pass(emu, res):
         assert counts[1] >= counts[2]                                           # every inside pixel is on a kept row
 
 
+def test_row_trim_with_giant_and_degenerate_triangles(emu):
+    """Triangles the error analysis must either cover or refuse: vertices 1e2 .. 1e6 pixels outside the frame (the bbox is clipped, the
+    Gram terms reach 1e12 .. 1e24 -- beyond the guards the slack terms become infinite and nothing may be trimmed), near-zero area,
+    and non-finite vertices (every comparison false)."""
+    emu.emu_row_trim_soundness.restype = ctypes.c_uint64
+    rng = np.random.default_rng(99)
+    res = (640, 480)
+    n = 3000
+    c = np.stack([rng.uniform(0, res[0], n), rng.uniform(0, res[1], n)], 1)
+    size = np.exp(rng.uniform(np.log(1e2), np.log(1e6), n))[:, None, None]
+    xy = c[:, None, :] + rng.uniform(-1, 1, (n, 3, 2)) * size
+    z = 0.5 + rng.uniform(-1, 1, (n, 3)) * np.exp(rng.uniform(np.log(1e-3), np.log(1e3), n))[:, None]
+    giant = np.concatenate([xy, z[:, :, None]], 2).astype(np.float32).reshape(n, 9)
+    thin = _adversarial_triangles(rng, 20_000, res)
+    thin.reshape(-1, 3, 3)[:, 2, :2] = thin.reshape(-1, 3, 3)[:, 0, :2] + (thin.reshape(-1, 3, 3)[:, 1, :2] - thin.reshape(-1, 3, 3)[:, 0, :2]) * rng.uniform(0, 1, (20_000, 1)).astype(np.float32)
+    bad = _adversarial_triangles(rng, 2_000, res)
+    bad[rng.integers(0, 2_000, 300), rng.integers(0, 9, 300)] = np.array([np.nan, np.inf, -np.inf], np.float32)[rng.integers(0, 3, 300)]
+    for tri in (giant, thin, bad):
+        counts = (ctypes.c_uint64 * 3)(0, 0, 0)
+        wrong = emu.emu_row_trim_soundness(np.ascontiguousarray(tri, np.float32).ctypes.data_as(_fp), tri.shape[0], res[0], res[1], counts)
+        assert wrong == 0, f"{wrong} rows that pass were trimmed away"
+        assert counts[1] >= counts[2]
+
+
 def test_row_trim_on_the_cfg5_sphere(emu):
     """The workload it is meant for: views of the 5 000-triangle sphere at 1080p -- no row that passes is removed, and the rows left are
     close to the pixels inside (the figure quoted in DESIGN.md)."""
