@@ -14,7 +14,9 @@
  *   - no barrier anywhere after the CTA's start-up: warps pull (view, tile, band) items from the work queue independently;
  *   - a triangle of any size goes through the same path: inside a band a large triangle is 8 units of up to 32 rows -- full
  *     lanes, uniform trip counts -- so the CTA-wide sweep of large triangles and its deferral lists are gone;
- *   - the frame is still written as full 128-byte column segments (a band column is 32 rows = 128 bytes).
+ *   - the frame is still written as full 128-byte column segments (a band column is 32 rows = 128 bytes);
+ *   - a triangle much larger than a band covers a chord of each of its bbox columns: before the row loop every unit trims its row
+ *     range to the rows that can pass the cheap tests (gel_math.h: row_trim, exact), which takes a third of the row iterations away.
  * The arithmetic per (triangle, pixel) -- and therefore every bit of the frames -- is that of raster_kernel (main.c:316-370);
  * so are the exact two-phase depth culling (near triangles first, far ones parked and tested against the band's own hi-Z) and the
  * TMA reset of untouched tiles.
