@@ -9,7 +9,7 @@ import bench
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 HEAD = "# ncu --set full --clock-control none --import-source on  (scripts/gpu_r2_evidence.sh), summarised by scripts/ncu_summary.py + scripts/ncu_lines.py\n"
 CAPS = {"r02_d1": "r02_ncu_d1.txt", "r02_d5": "r02_ncu_d5.txt", "r02_d5a": "r02_ncu_d5a.txt", "r02_d2": "r02_ncu_d2.txt", "r02_d0": "r02_ncu_d0.txt", "r02_transform_cfg3": "r02_ncu_transform_cfg3.txt",
-        "r02_raster_cfg5": "r02_ncu_raster_cfg5.txt", "r02_bin_cfg5": "r02_ncu_bin_cfg5.txt", "r02_raster_cfg2": "r02_ncu_raster_cfg2.txt", "r02_raster_cfg1": "r02_ncu_raster_cfg1.txt"}
+        "r02_raster_cfg5": "r02_ncu_raster_cfg5.txt", "r02_bin_cfg5": "r02_ncu_bin_cfg5.txt", "r02_raster_cfg2": "r02_ncu_raster_cfg2.txt", "r02_raster_cfg1": "r02_ncu_raster_cfg1.txt", "r02_d1_cfg4": "r02_ncu_d1_cfg4.txt"}
 
 
 def raw(rep):
@@ -39,7 +39,7 @@ for src, dst in (("r02_bench_cfg3.json", "r02_bench_cfg3.json"), ("r02_bench_ref
 
 def per_frame(cap, pick=0): r = traffic[cap][pick]; return int((r[1] + r[2]) / 64), f"{r[1] / 1e6:.1f} MB read + {r[2] / 1e6:.1f} MB written over 64 frames"
 recs = []
-for kernel, wl, cap, txt in (("direct_raster_kernel<0>", "cfg3", "r02_d1", "r02_ncu_d1.txt"), ("raster_band_kernel", "cfg5", "r02_raster_cfg5", "r02_ncu_raster_cfg5.txt"),
+for kernel, wl, cap, txt in (("direct_raster_kernel<0>", "cfg3", "r02_d1", "r02_ncu_d1.txt"), ("direct_raster_kernel<0>", "cfg4", "r02_d1_cfg4", "r02_ncu_d1_cfg4.txt"), ("raster_band_kernel", "cfg5", "r02_raster_cfg5", "r02_ncu_raster_cfg5.txt"),
                              ("raster_band_kernel", "cfg2", "r02_raster_cfg2", "r02_ncu_raster_cfg2.txt"), ("raster_band_kernel", "cfg1", "r02_raster_cfg1", "r02_ncu_raster_cfg1.txt")):
     if cap in traffic:
         b, how = per_frame(cap); recs.append({"kernel": kernel, "workload": wl, "bytes_per_frame": b, "from": f"{txt}: {how}"})
